@@ -1,0 +1,59 @@
+// asz_engine.hpp -- host-side engine object behind the C ABI (include/asz_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/asz_b200.h"
+
+namespace asz {
+
+void set_error(const std::string& msg);
+bool cuda_ok(cudaError_t err, const char* what);
+
+#define ASZ_CUDA(call)                                         \
+  do {                                                         \
+    if (!::asz::cuda_ok((call), #call)) return ASZ_ERR_CUDA;   \
+  } while (0)
+
+struct SearchState;   // asz_mcts.cu
+
+// Device-resident game set: one record per game, structure-of-arrays over games.
+//   cells  [n][PC]  u16 stamps (asz_common.cuh)
+//   snakes [n][8]   u64 packed snake records
+//   meta   [n][8]   u32 turn, episode, wall, body, head, starve, food_eaten, flags
+struct GameSet {
+  int n = 0;
+  uint16_t* cells = nullptr;
+  uint64_t* snakes = nullptr;
+  uint32_t* meta = nullptr;
+};
+
+}  // namespace asz
+
+struct asz_engine {
+  asz_config cfg;
+  int device = 0;
+  int pc = 0;            // padded cells per game
+  int plane = 0;         // floats per plane
+  uint32_t chance_thresh = 0;
+  asz::GameSet root;
+  // env-step scratch owned by the engine
+  float* planes = nullptr;        // [G*S][plane]
+  int32_t* row_ids = nullptr;     // [G*S]
+  int32_t* row_count = nullptr;   // [1]
+  uint8_t* actions = nullptr;     // [G*8]
+  int32_t* spawn_cells = nullptr; // [G]
+  uint8_t* ended = nullptr;       // [G]
+  int8_t* rewards = nullptr;      // [G*8]
+  unsigned long long* totals = nullptr;  // [8]
+  asz::SearchState* search = nullptr;
+};
+
+namespace asz {
+int gameset_alloc(GameSet& gs, int n, int pc);
+void gameset_free(GameSet& gs);
+int search_create(asz_engine* e);
+void search_destroy(asz_engine* e);
+}  // namespace asz

@@ -1,0 +1,450 @@
+// asz_env.cu -- lockstep Battlesnake tic with the plane encoding fused in, plus the env part of the C ABI.
+//
+// Kernel: one warp per game, WARPS games per CTA.  Per launch a warp loads its game record (cells + snakes + meta,
+// ~320 B at 11x11x4), steps it in shared memory (asz_game.cuh), writes the record back, and streams the plane of
+// every surviving snake (5,292 B each at 11x11) straight into the network's input batch with 16-byte stores.
+// Rows of the batch are handed out by one atomicAdd per CTA after a block-level scan of the live counts.
+// Roofline: HBM write bandwidth (planes are > 95 % of the bytes).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "asz_engine.hpp"
+#include "asz_game.cuh"
+
+namespace asz {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+bool cuda_ok(cudaError_t err, const char* what) {
+  if (err == cudaSuccess) return true;
+  g_err = std::string(what) + ": " + cudaGetErrorString(err);
+  return false;
+}
+
+struct EnvParams {
+  uint16_t* cells; uint64_t* snakes; uint32_t* meta;
+  int G, S, health_dec;
+  uint32_t flags; int spawn_mode; uint32_t chance_thresh; uint64_t seed;
+  const uint8_t* actions; const int32_t* spawn_cells;
+  float* planes; int32_t* row_ids; uint64_t* keys; int max_rows; int32_t* row_count;
+  uint8_t* ended; int8_t* rewards; unsigned long long* totals;
+};
+
+// ---- record load / store ------------------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ void load_board(const uint16_t* __restrict__ gcells, uint16_t* sb, int lane) {
+  if constexpr (G::CPL % 4 == 0) {
+    const uint2* src = reinterpret_cast<const uint2*>(gcells);
+    uint2* dst = reinterpret_cast<uint2*>(sb);
+#pragma unroll
+    for (int q = 0; q < G::CPL / 4; ++q) dst[lane * (G::CPL / 4) + q] = src[lane * (G::CPL / 4) + q];
+  } else {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gcells);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sb);
+#pragma unroll
+    for (int q = 0; q < G::CPL / 2; ++q) dst[lane * (G::CPL / 2) + q] = src[lane * (G::CPL / 2) + q];
+  }
+}
+__device__ __forceinline__ Meta load_meta(const uint32_t* __restrict__ gm, int lane) {
+  const uint32_t v = (lane < 8) ? gm[lane] : 0u;
+  Meta m;
+  m.turn = __shfl_sync(kFull, v, 0); m.episode = __shfl_sync(kFull, v, 1); m.wall = __shfl_sync(kFull, v, 2);
+  m.body = __shfl_sync(kFull, v, 3); m.headc = __shfl_sync(kFull, v, 4); m.starve = __shfl_sync(kFull, v, 5);
+  m.eaten = __shfl_sync(kFull, v, 6); m.flags = __shfl_sync(kFull, v, 7);
+  return m;
+}
+__device__ __forceinline__ void store_meta(uint32_t* gm, const Meta& m, int lane) {
+  if (lane < 8) {
+    const uint32_t v = lane == 0 ? m.turn : lane == 1 ? m.episode : lane == 2 ? m.wall : lane == 3 ? m.body
+                     : lane == 4 ? m.headc : lane == 5 ? m.starve : lane == 6 ? m.eaten : m.flags;
+    gm[lane] = v;
+  }
+}
+
+// ---- the fused step kernel ----------------------------------------------------------------------------------------
+template <int SIDE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) env_step_kernel(const EnvParams p) {
+  using G = Geo<SIDE>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_cnt[WARPS];
+  __shared__ int s_base;
+  __shared__ unsigned long long s_tot[8];
+  const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
+  float* stage = reinterpret_cast<float*>(smem_raw) + warp * G::STAGE;
+  uint16_t* sb = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * G::STAGE * sizeof(float)) + warp * G::PC;
+  if (threadIdx.x < 8) s_tot[threadIdx.x] = 0ull;
+  __syncthreads();
+
+  const int g = (int)blockIdx.x * WARPS + warp;
+  const bool valid = g < p.G;
+  Snake sn; sn.head = 0xFFFF; sn.len = 0; sn.health = 0; sn.last = 0; sn.alive = 0; sn.reward = 0;
+  Meta m; m.turn = m.episode = m.wall = m.body = m.headc = m.starve = m.eaten = 0; m.flags = 1;
+  if (valid) {
+    load_board<G>(p.cells + (size_t)g * G::PC, sb, lane);
+    if (lane < 8) sn = unpack_snake(p.snakes[(size_t)g * 8 + lane]);
+    m = load_meta(p.meta + (size_t)g * 8, lane);
+    __syncwarp();
+    if ((p.flags & ASZ_STEP_TIC) && !(m.flags & 1u)) {
+      int move = 1;
+      if (p.flags & ASZ_STEP_RANDOM_ACT) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)g, m.episode, (lane & 4) ? RS_ACT_HI : RS_ACT_LO, m.turn, p.seed, r);
+        const uint32_t rv = (lane & 3) == 0 ? r[0] : (lane & 3) == 1 ? r[1] : (lane & 3) == 2 ? r[2] : r[3];
+        move = (int)mulhi32(rv, 3u);
+      } else if (lane < 8) {
+        move = (int)p.actions[(size_t)g * 8 + lane];
+      }
+      const int spawn_cell = (p.spawn_mode == ASZ_SPAWN_REPLAY) ? p.spawn_cells[g] : -1;
+      const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, p.spawn_mode, spawn_cell, p.chance_thresh, p.seed,
+                                      (uint32_t)g);
+      if (p.rewards != nullptr && lane < 8)
+        p.rewards[(size_t)g * 8 + lane] = (int8_t)(sn.reward == 1 ? 1 : sn.reward == 2 ? -1 : 0);
+      if (lane == 0) {
+        if (p.ended != nullptr) p.ended[g] = r.ended ? 1 : 0;
+        atomicAdd(&s_tot[7], 1ull);
+        if (r.ended) {   // mp_game_runner.py:56-61
+          atomicAdd(&s_tot[0], (unsigned long long)m.wall); atomicAdd(&s_tot[1], (unsigned long long)m.body);
+          atomicAdd(&s_tot[2], (unsigned long long)m.headc); atomicAdd(&s_tot[3], (unsigned long long)m.starve);
+          atomicAdd(&s_tot[4], (unsigned long long)m.eaten); atomicAdd(&s_tot[5], (unsigned long long)m.turn);
+          atomicAdd(&s_tot[6], 1ull);
+        }
+      }
+      if (r.ended && (p.flags & ASZ_STEP_AUTO_RESET)) warp_init_native<G>(sb, sn, m, p.S, p.seed, (uint32_t)g, m.episode + 1);
+      // write the record back
+      {
+        uint16_t* gc = p.cells + (size_t)g * G::PC;
+        if constexpr (G::CPL % 4 == 0) {
+#pragma unroll
+          for (int q = 0; q < G::CPL / 4; ++q)
+            reinterpret_cast<uint2*>(gc)[lane * (G::CPL / 4) + q] = reinterpret_cast<const uint2*>(sb)[lane * (G::CPL / 4) + q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < G::CPL / 2; ++q)
+            reinterpret_cast<uint32_t*>(gc)[lane * (G::CPL / 2) + q] = reinterpret_cast<const uint32_t*>(sb)[lane * (G::CPL / 2) + q];
+        }
+        if (lane < 8) p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
+        store_meta(p.meta + (size_t)g * 8, m, lane);
+      }
+    } else if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) {
+      p.ended[g] = 0;
+    }
+  }
+  // ---- row allocation: block scan of live counts, one atomic per CTA ----
+  const unsigned live_mask = __ballot_sync(kFull, sn.alive != 0);
+  const bool do_encode = (p.flags & ASZ_STEP_ENCODE) && valid && !(m.flags & 1u);
+  const int n_rows = do_encode ? __popc(live_mask) : 0;
+  if (lane == 0) s_cnt[warp] = n_rows;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+    s_base = tot > 0 ? atomicAdd(p.row_count, tot) : 0;
+    if (tot > 0) atomicAdd(&p.totals[8], (unsigned long long)tot);
+  }
+  if (threadIdx.x < 8 && s_tot[threadIdx.x] != 0ull) atomicAdd(&p.totals[threadIdx.x], s_tot[threadIdx.x]);
+  __syncthreads();
+  if (n_rows == 0) return;
+  int row = s_base + s_cnt[warp];
+  CellView<G> cv;
+  warp_cell_view<G>(sb, sn, cv);
+  unsigned rest = live_mask;
+  while (rest) {
+    const int vs = __ffs(rest) - 1;
+    rest &= rest - 1;
+    if (row < p.max_rows) {
+      uint64_t k0 = 0, k1 = 0;
+      if (p.flags & ASZ_STEP_KEYS) {
+        warp_encode<G, true>(cv, sn, vs, stage, p.planes, (size_t)row * G::PLANE, &k0, &k1);
+        if (lane == 0) { p.keys[2 * (size_t)row] = k0; p.keys[2 * (size_t)row + 1] = k1; }
+      } else {
+        warp_encode<G, false>(cv, sn, vs, stage, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
+      }
+      if (lane == 0) p.row_ids[row] = g * 8 + vs;
+    }
+    ++row;
+  }
+}
+
+// ---- reset kernel ---------------------------------------------------------------------------------------------------
+template <int SIDE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) env_reset_kernel(uint16_t* cells, uint64_t* snakes, uint32_t* meta, int Gn,
+                                                               int S, uint64_t seed) {
+  using G = Geo<SIDE>;
+  __shared__ __align__(16) uint16_t s_board[WARPS][G::PC];
+  const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
+  const int g = (int)blockIdx.x * WARPS + warp;
+  if (g >= Gn) return;
+  uint16_t* sb = s_board[warp];
+  Snake sn; Meta m;
+  warp_init_native<G>(sb, sn, m, S, seed, (uint32_t)g, 0);
+#pragma unroll
+  for (int q = 0; q < G::CPL; ++q) cells[(size_t)g * G::PC + lane * G::CPL + q] = sb[lane * G::CPL + q];
+  if (lane < 8) snakes[(size_t)g * 8 + lane] = pack_snake(sn);
+  store_meta(meta + (size_t)g * 8, m, lane);
+}
+
+template <int SIDE>
+struct EnvLaunch {
+  static constexpr int WARPS = (SIDE >= 19) ? 4 : 8;
+  using G = Geo<SIDE>;
+  static size_t smem_bytes() { return (size_t)WARPS * (G::STAGE * sizeof(float) + G::PC * sizeof(uint16_t)); }
+  static int step(const EnvParams& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_bytes()), "cudaFuncSetAttribute(env_step_kernel)"))
+        return ASZ_ERR_CUDA;
+      configured = true;
+    }
+    const int blocks = (p.G + WARPS - 1) / WARPS;
+    env_step_kernel<SIDE, WARPS><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
+    return cuda_ok(cudaGetLastError(), "env_step_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
+  }
+  static int reset(const GameSet& gs, int S, uint64_t seed, cudaStream_t st) {
+    const int blocks = (gs.n + WARPS - 1) / WARPS;
+    env_reset_kernel<SIDE, WARPS><<<blocks, WARPS * 32, 0, st>>>(gs.cells, gs.snakes, gs.meta, gs.n, S, seed);
+    return cuda_ok(cudaGetLastError(), "env_reset_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
+  }
+};
+
+int gameset_alloc(GameSet& gs, int n, int pc) {
+  gs.n = n;
+  ASZ_CUDA(cudaMalloc(&gs.cells, (size_t)n * pc * sizeof(uint16_t)));
+  ASZ_CUDA(cudaMalloc(&gs.snakes, (size_t)n * 8 * sizeof(uint64_t)));
+  ASZ_CUDA(cudaMalloc(&gs.meta, (size_t)n * 8 * sizeof(uint32_t)));
+  ASZ_CUDA(cudaMemset(gs.cells, 0, (size_t)n * pc * sizeof(uint16_t)));
+  ASZ_CUDA(cudaMemset(gs.snakes, 0, (size_t)n * 8 * sizeof(uint64_t)));
+  ASZ_CUDA(cudaMemset(gs.meta, 0, (size_t)n * 8 * sizeof(uint32_t)));
+  return ASZ_OK;
+}
+void gameset_free(GameSet& gs) {
+  cudaFree(gs.cells); cudaFree(gs.snakes); cudaFree(gs.meta);
+  gs = GameSet();
+}
+
+static int pc_of(int side) { return side == 7 ? Geo<7>::PC : side == 11 ? Geo<11>::PC : Geo<19>::PC; }
+
+}  // namespace asz
+
+using namespace asz;
+
+extern "C" {
+
+const char* asz_last_error(void) { return g_err.c_str(); }
+int asz_version(void) { return ASZ_VERSION; }
+
+int asz_engine_create(asz_engine** out, const asz_config* cfg) {
+  if (!out || !cfg) { set_error("asz_engine_create: null argument"); return ASZ_ERR_ARG; }
+  if (cfg->side != 7 && cfg->side != 11 && cfg->side != 19) { set_error("side must be 7, 11 or 19"); return ASZ_ERR_ARG; }
+  if (cfg->snakes < 1 || cfg->snakes > ASZ_MAX_SNAKES) { set_error("snakes must be in 1..8"); return ASZ_ERR_ARG; }
+  if (cfg->games < 1) { set_error("games must be >= 1"); return ASZ_ERR_ARG; }
+  if (cfg->health_dec < 0 || cfg->health_dec > 100) { set_error("health_dec out of range"); return ASZ_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this engine has no CPU fallback");
+    return ASZ_ERR_CUDA;
+  }
+  asz_engine* e = new asz_engine();
+  e->cfg = *cfg;
+  ASZ_CUDA(cudaGetDevice(&e->device));
+  e->pc = pc_of(cfg->side);
+  e->plane = (2 * cfg->side - 1) * (2 * cfg->side - 1) * 3;
+  double th = (double)cfg->food_chance * 4294967296.0;
+  e->chance_thresh = th <= 0.0 ? 0u : th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
+  const size_t G = (size_t)cfg->games, rows = G * (size_t)cfg->snakes;
+  int rc = gameset_alloc(e->root, cfg->games, e->pc);
+  if (rc != ASZ_OK) { delete e; return rc; }
+  ASZ_CUDA(cudaMalloc(&e->planes, rows * (size_t)e->plane * sizeof(float) + 16));
+  ASZ_CUDA(cudaMalloc(&e->row_ids, rows * sizeof(int32_t)));
+  ASZ_CUDA(cudaMalloc(&e->row_count, sizeof(int32_t)));
+  ASZ_CUDA(cudaMalloc(&e->actions, G * 8));
+  ASZ_CUDA(cudaMalloc(&e->spawn_cells, G * sizeof(int32_t)));
+  ASZ_CUDA(cudaMalloc(&e->ended, G));
+  ASZ_CUDA(cudaMalloc(&e->rewards, G * 8));
+  ASZ_CUDA(cudaMalloc(&e->totals, 16 * sizeof(unsigned long long)));
+  ASZ_CUDA(cudaMemset(e->totals, 0, 16 * sizeof(unsigned long long)));
+  ASZ_CUDA(cudaMemset(e->ended, 0, G));
+  ASZ_CUDA(cudaMemset(e->rewards, 0, G * 8));
+  ASZ_CUDA(cudaMemset(e->actions, 1, G * 8));
+  if (cfg->max_breadth > 0) {
+    rc = search_create(e);
+    if (rc != ASZ_OK) { asz_engine_destroy(e); return rc; }
+  }
+  *out = e;
+  return ASZ_OK;
+}
+
+int asz_engine_destroy(asz_engine* e) {
+  if (!e) return ASZ_OK;
+  search_destroy(e);
+  gameset_free(e->root);
+  cudaFree(e->planes); cudaFree(e->row_ids); cudaFree(e->row_count); cudaFree(e->actions); cudaFree(e->spawn_cells);
+  cudaFree(e->ended); cudaFree(e->rewards); cudaFree(e->totals);
+  delete e;
+  return ASZ_OK;
+}
+
+int asz_reset(asz_engine* e, void* stream) {
+  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  ASZ_CUDA(cudaMemsetAsync(e->totals, 0, 16 * sizeof(unsigned long long), st));
+  switch (e->cfg.side) {
+    case 7: return EnvLaunch<7>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
+    case 11: return EnvLaunch<11>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
+    default: return EnvLaunch<19>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
+  }
+}
+
+int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
+  if (!e || !a) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if ((a->flags & ASZ_STEP_ENCODE) && (!a->d_planes || !a->d_row_ids || !a->d_row_count || a->max_rows <= 0)) {
+    set_error("ASZ_STEP_ENCODE needs d_planes, d_row_ids, d_row_count and max_rows"); return ASZ_ERR_ARG;
+  }
+  if ((a->flags & ASZ_STEP_ENCODE) && ((uintptr_t)a->d_planes & 15u)) { set_error("d_planes must be 16-byte aligned"); return ASZ_ERR_ARG; }
+  if ((a->flags & ASZ_STEP_KEYS) && !a->d_keys) { set_error("ASZ_STEP_KEYS needs d_keys"); return ASZ_ERR_ARG; }
+  if ((a->flags & ASZ_STEP_TIC) && !(a->flags & ASZ_STEP_RANDOM_ACT) && !a->d_actions) { set_error("d_actions is null"); return ASZ_ERR_ARG; }
+  if ((a->flags & ASZ_STEP_TIC) && a->spawn_mode == ASZ_SPAWN_REPLAY && !a->d_spawn_cells) { set_error("d_spawn_cells is null"); return ASZ_ERR_ARG; }
+  if (a->spawn_mode < 0 || a->spawn_mode > 2) { set_error("bad spawn_mode"); return ASZ_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  EnvParams p;
+  p.cells = e->root.cells; p.snakes = e->root.snakes; p.meta = e->root.meta;
+  p.G = e->cfg.games; p.S = e->cfg.snakes; p.health_dec = e->cfg.health_dec;
+  p.flags = a->flags; p.spawn_mode = a->spawn_mode; p.chance_thresh = e->chance_thresh; p.seed = e->cfg.seed;
+  p.actions = a->d_actions; p.spawn_cells = a->d_spawn_cells;
+  p.planes = a->d_planes; p.row_ids = a->d_row_ids; p.keys = a->d_keys; p.max_rows = a->max_rows;
+  p.row_count = a->d_row_count ? a->d_row_count : e->row_count;
+  p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals;
+  ASZ_CUDA(cudaMemsetAsync(p.row_count, 0, sizeof(int32_t), st));
+  switch (e->cfg.side) {
+    case 7: return EnvLaunch<7>::step(p, st);
+    case 11: return EnvLaunch<11>::step(p, st);
+    default: return EnvLaunch<19>::step(p, st);
+  }
+}
+
+int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
+                      const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, int32_t* h_row_count,
+                      float* h_planes, int32_t* h_row_ids, void* stream) {
+  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t G = (size_t)e->cfg.games;
+  if ((flags & ASZ_STEP_TIC) && !(flags & ASZ_STEP_RANDOM_ACT)) {
+    if (!h_actions) { set_error("h_actions is null"); return ASZ_ERR_ARG; }
+    ASZ_CUDA(cudaMemcpyAsync(e->actions, h_actions, G * 8, cudaMemcpyHostToDevice, st));
+  }
+  if ((flags & ASZ_STEP_TIC) && spawn_mode == ASZ_SPAWN_REPLAY) {
+    if (!h_spawn_cells) { set_error("h_spawn_cells is null"); return ASZ_ERR_ARG; }
+    ASZ_CUDA(cudaMemcpyAsync(e->spawn_cells, h_spawn_cells, G * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  asz_step_args a;
+  memset(&a, 0, sizeof a);
+  a.flags = flags; a.spawn_mode = spawn_mode; a.d_actions = e->actions; a.d_spawn_cells = e->spawn_cells;
+  a.d_planes = e->planes; a.d_row_ids = e->row_ids; a.max_rows = (int32_t)(G * (size_t)e->cfg.snakes);
+  a.d_row_count = e->row_count; a.d_ended = e->ended; a.d_rewards = e->rewards;
+  int rc = asz_env_step(e, &a, stream);
+  if (rc != ASZ_OK) return rc;
+  if (h_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, e->ended, G, cudaMemcpyDeviceToHost, st));
+  if (h_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, e->rewards, G * 8, cudaMemcpyDeviceToHost, st));
+  int32_t rows = 0;
+  ASZ_CUDA(cudaMemcpyAsync(&rows, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  ASZ_CUDA(cudaStreamSynchronize(st));
+  if (h_row_count) *h_row_count = rows;
+  if ((h_planes || h_row_ids) && rows > 0) {
+    if (h_planes) ASZ_CUDA(cudaMemcpyAsync(h_planes, e->planes, (size_t)rows * e->plane * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_row_ids) ASZ_CUDA(cudaMemcpyAsync(h_row_ids, e->row_ids, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ASZ_CUDA(cudaStreamSynchronize(st));
+  }
+  return ASZ_OK;
+}
+
+int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
+  if (!e || !h_totals) { set_error("null argument"); return ASZ_ERR_ARG; }
+  ASZ_CUDA(cudaDeviceSynchronize());
+  ASZ_CUDA(cudaMemcpy(h_totals, e->totals, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return ASZ_OK;
+}
+
+float* asz_internal_planes(asz_engine* e) { return e ? e->planes : nullptr; }
+int32_t* asz_internal_row_ids(asz_engine* e) { return e ? e->row_ids : nullptr; }
+size_t asz_plane_floats(const asz_engine* e) { return e ? (size_t)e->plane : 0; }
+
+// ---- state interchange (host side conversion between the canonical dump and the packed records) ----------------
+static int gs_get_state(const asz_config& cfg, int pc, const GameSet& gs, int32_t game, int32_t* h_snake, int32_t* h_owner,
+                        int32_t* h_dist, int32_t* h_food, int32_t* h_counters) {
+  if (game < 0 || game >= gs.n) { set_error("game index out of range"); return ASZ_ERR_ARG; }
+  const int C = cfg.side * cfg.side;
+  std::vector<uint16_t> cells(pc);
+  uint64_t sn[8]; uint32_t meta[8];
+  ASZ_CUDA(cudaDeviceSynchronize());
+  ASZ_CUDA(cudaMemcpy(cells.data(), gs.cells + (size_t)game * pc, pc * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  ASZ_CUDA(cudaMemcpy(sn, gs.snakes + (size_t)game * 8, sizeof sn, cudaMemcpyDeviceToHost));
+  ASZ_CUDA(cudaMemcpy(meta, gs.meta + (size_t)game * 8, sizeof meta, cudaMemcpyDeviceToHost));
+  for (int c = 0; c < C; ++c) {
+    const uint16_t v = cells[c];
+    h_food[c] = v == 0x8000u; h_owner[c] = -1; h_dist[c] = 0;
+    if (v != 0 && v != 0x8000u) { h_owner[c] = (v >> 12) & 7; h_dist[c] = v & 0x0fff; }
+  }
+  for (int s = 0; s < cfg.snakes; ++s) {
+    const uint64_t v = sn[s];
+    int32_t* o = h_snake + 6 * s;
+    const int head = (int)(v & 0xFFFF), rw = (int)((v >> 43) & 3);
+    o[0] = (int)((v >> 42) & 1); o[1] = (int)((v >> 32) & 0xFF); o[2] = (int)((v >> 16) & 0xFFFF);
+    o[3] = (int)((v >> 40) & 3); o[4] = head == 0xFFFF ? -1 : head; o[5] = rw == 1 ? 1 : rw == 2 ? -1 : 0;
+  }
+  for (int k = 0; k < 5; ++k) h_counters[k] = (int32_t)meta[2 + k];
+  h_counters[5] = (int32_t)meta[0]; h_counters[6] = (int32_t)meta[1]; h_counters[7] = (int32_t)(meta[7] & 1u);
+  return ASZ_OK;
+}
+
+static int gs_set_state(const asz_config& cfg, int pc, GameSet& gs, int32_t game, const int32_t* h_snake,
+                        const int32_t* h_owner, const int32_t* h_dist, const int32_t* h_food, const int32_t* h_counters) {
+  if (game < 0 || game >= gs.n) { set_error("game index out of range"); return ASZ_ERR_ARG; }
+  const int C = cfg.side * cfg.side;
+  std::vector<uint16_t> cells(pc, 0);
+  uint64_t sn[8] = {0}; uint32_t meta[8] = {0};
+  for (int c = 0; c < C; ++c) {
+    if (h_food[c]) cells[c] = 0x8000u;
+    else if (h_owner[c] >= 0) {
+      if (h_owner[c] >= cfg.snakes || h_dist[c] <= 0 || h_dist[c] > 0x0fff) { set_error("bad cell stamp"); return ASZ_ERR_ARG; }
+      cells[c] = (uint16_t)((h_owner[c] << 12) | h_dist[c]);
+    }
+  }
+  int live = 0;
+  for (int s = 0; s < 8; ++s) {
+    uint64_t v = 0xFFFFull;
+    if (s < cfg.snakes) {
+      const int32_t* o = h_snake + 6 * s;
+      const int alive = o[0] != 0;
+      live += alive;
+      const int head = (alive && o[4] >= 0) ? o[4] : 0xFFFF;
+      const int rw = o[5] > 0 ? 1 : o[5] < 0 ? 2 : 0;
+      v = (uint64_t)(head & 0xFFFF) | ((uint64_t)((alive ? o[2] : 0) & 0xFFFF) << 16) | ((uint64_t)((alive ? o[1] : 0) & 0xFF) << 32) |
+          ((uint64_t)(o[3] & 3) << 40) | ((uint64_t)alive << 42) | ((uint64_t)rw << 43);
+    }
+    sn[s] = v;
+  }
+  meta[0] = (uint32_t)h_counters[5]; meta[1] = (uint32_t)h_counters[6];
+  for (int k = 0; k < 5; ++k) meta[2 + k] = (uint32_t)h_counters[k];
+  meta[7] = (h_counters[7] != 0 || live <= 1) ? 1u : 0u;
+  ASZ_CUDA(cudaDeviceSynchronize());
+  ASZ_CUDA(cudaMemcpy(gs.cells + (size_t)game * pc, cells.data(), pc * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  ASZ_CUDA(cudaMemcpy(gs.snakes + (size_t)game * 8, sn, sizeof sn, cudaMemcpyHostToDevice));
+  ASZ_CUDA(cudaMemcpy(gs.meta + (size_t)game * 8, meta, sizeof meta, cudaMemcpyHostToDevice));
+  return ASZ_OK;
+}
+
+int asz_get_state(asz_engine* e, int32_t game, int32_t* h_snake, int32_t* h_owner, int32_t* h_dist, int32_t* h_food,
+                  int32_t* h_counters) {
+  if (!e || !h_snake || !h_owner || !h_dist || !h_food || !h_counters) { set_error("null argument"); return ASZ_ERR_ARG; }
+  return gs_get_state(e->cfg, e->pc, e->root, game, h_snake, h_owner, h_dist, h_food, h_counters);
+}
+int asz_set_state(asz_engine* e, int32_t game, const int32_t* h_snake, const int32_t* h_owner, const int32_t* h_dist,
+                  const int32_t* h_food, const int32_t* h_counters) {
+  if (!e || !h_snake || !h_owner || !h_dist || !h_food || !h_counters) { set_error("null argument"); return ASZ_ERR_ARG; }
+  return gs_set_state(e->cfg, e->pc, e->root, game, h_snake, h_owner, h_dist, h_food, h_counters);
+}
+
+}  // extern "C"

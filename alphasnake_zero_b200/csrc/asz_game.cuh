@@ -1,0 +1,328 @@
+// asz_game.cuh -- one warp = one Battlesnake game.  Warp-level restatement of Game.__init__, Game.tic and
+// Game.make_state (reference: code/utils/game.py:13-61, 87-205, 215-257) over the cell-stamp board of asz_common.cuh.
+//
+// Thread mapping: lane s (< S <= 8) owns snake s; every lane owns CPL consecutive cells of the board, so that
+// row-major cell order equals (lane, slot) order (used by the k-th-empty-cell food spawn).
+// The board lives in shared memory while a game is being stepped (random access by head cells), the per-snake and
+// per-game scalars live in registers.
+#pragma once
+#include "asz_common.cuh"
+
+namespace asz {
+
+template <int SIDE_>
+struct Geo {
+  static constexpr int SIDE = SIDE_;
+  static constexpr int CELLS = SIDE * SIDE;
+  static constexpr int CPL = (CELLS + 31) / 32;  // cells per lane
+  static constexpr int PC = CPL * 32;            // padded cell count (state stride, u16 units)
+  static constexpr int N = 2 * SIDE - 1;         // side of the egocentric plane (game.py:217-218)
+  static constexpr int NPIX = N * N;
+  static constexpr int PLANE = NPIX * 3;         // floats per plane, NHWC
+  static constexpr int STAGE = ((PLANE + 3 + 3) / 4) * 4;  // staging floats (plane + up to 3 of misalignment)
+};
+
+// ---- packed records in HBM ---------------------------------------------------------------------------------------
+// snake: head:16 | len:16 | health:8 | last_move:2 | alive:1 | reward:2 (0 none, 1 = +1, 2 = -1)
+struct Snake {
+  int head;    // cell index, 0xFFFF = none
+  int len;
+  int health;
+  int last;
+  int alive;
+  int reward;
+};
+__device__ __forceinline__ uint64_t pack_snake(const Snake& s) {
+  return (uint64_t)(s.head & 0xFFFF) | ((uint64_t)(s.len & 0xFFFF) << 16) | ((uint64_t)(s.health & 0xFF) << 32) |
+         ((uint64_t)(s.last & 3) << 40) | ((uint64_t)(s.alive & 1) << 42) | ((uint64_t)(s.reward & 3) << 43);
+}
+__device__ __forceinline__ Snake unpack_snake(uint64_t v) {
+  Snake s;
+  s.head = (int)(v & 0xFFFF); s.len = (int)((v >> 16) & 0xFFFF); s.health = (int)((v >> 32) & 0xFF);
+  s.last = (int)((v >> 40) & 3); s.alive = (int)((v >> 42) & 1); s.reward = (int)((v >> 43) & 3);
+  return s;
+}
+// game meta: 8 x u32 = turn(game_length), episode, wall, body, head, starve, food_eaten, flags (bit0 = done)
+struct Meta {
+  uint32_t turn, episode, wall, body, headc, starve, eaten, flags;
+};
+
+struct TicResult {
+  unsigned live_mask;   // snakes alive after the tic
+  unsigned dead_mask;   // snakes that died this tic
+  bool ended;           // <= 1 snake left (game.py:199)
+};
+
+// ---- Game.__init__ (game.py:13-61) with the engine's Philox streams -------------------------------------------
+template <class G>
+__device__ __forceinline__ void warp_init_native(uint16_t* sb, Snake& sn, Meta& m, int S, uint64_t seed, uint32_t game_id,
+                                                 uint32_t episode) {
+  const int lane = lane_id();
+  uint32_t u[8], v[8], w[8];
+  philox4x32_10(game_id, episode, RS_INIT, 0, seed, u); philox4x32_10(game_id, episode, RS_INIT, 1, seed, u + 4);
+  philox4x32_10(game_id, episode, RS_INIT, 2, seed, v); philox4x32_10(game_id, episode, RS_INIT, 3, seed, v + 4);
+  philox4x32_10(game_id, episode, RS_INIT, 4, seed, w); philox4x32_10(game_id, episode, RS_INIT, 5, seed, w + 4);
+  constexpr int H = G::SIDE, W = G::SIDE;
+  // the 8 standard start cells in the reference's order (game.py:25-28), as cell indices
+  int perm[8] = {1 * W + 1, (H - 2) * W + (W - 2), (H - 2) * W + 1, 1 * W + (W - 2),
+                 1 * W + W / 2, (H / 2) * W + (W - 2), (H - 2) * W + W / 2, (H / 2) * W + 1};
+  int my_start = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {   // partial Fisher-Yates == sample without replacement (game.py:25-29)
+    if (i < S) {
+      const int j = i + (int)mulhi32(u[i], (uint32_t)(8 - i));
+      int pj = perm[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) if (q == j) pj = perm[q];
+      const int pi = perm[i];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (q == j) perm[q] = pi;
+      perm[i] = pj;
+      if (lane == i) my_start = pj;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < G::CPL; ++q) sb[lane * G::CPL + q] = 0;
+  __syncwarp();
+  sn.head = 0xFFFF; sn.len = 0; sn.health = 0; sn.last = 0; sn.alive = 0; sn.reward = 0;
+  if (lane == 0) sb[(H / 2) * W + W / 2] = kFood;                     // game.py:43
+  if (lane < S) {
+    uint32_t vv = v[0], ww = w[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) if (q == lane) { vv = v[q]; ww = w[q]; }
+    sn.head = my_start; sn.len = 3; sn.health = 100; sn.last = (int)(vv & 3u); sn.alive = 1;   // game.py:30,37
+    const int d = (int)(ww & 3u);                                      // game.py:46-47 list order
+    const int fy = my_start / W + ((d & 2) ? 1 : -1), fx = my_start % W + ((d & 1) ? 1 : -1);
+    sb[fy * W + fx] = kFood;
+  }
+  __syncwarp();
+  if (lane < S) sb[my_start] = (uint16_t)((lane << 12) | 3);          // three stacked segments: topmost has dist 3
+  __syncwarp();
+  m.turn = 0; m.episode = episode; m.wall = m.body = m.headc = m.starve = m.eaten = 0; m.flags = 0;
+}
+
+// ---- Game.tic (game.py:87-205) -----------------------------------------------------------------------------------
+// move: this lane's relative move (0 left, 1 straight, 2 right), read only where sn.alive.
+// spawn_mode 0: none (sub-games, game.py:268), 1: replay (spawn_cell or -1), 2: native Philox.
+template <class G>
+__device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, int move, int health_dec, int spawn_mode,
+                                              int spawn_cell, uint32_t chance_thresh, uint64_t seed, uint32_t game_id) {
+  constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS;
+  const int lane = lane_id();
+  const bool was_alive = sn.alive != 0;
+  // 1. move (game.py:90-114, Snake.move :329-358) and 2. health (:117-118)
+  int nh = -1;
+  bool off = false;
+  if (was_alive) {
+    const int dir = (move + sn.last + 3) & 3;                 // (m + last - 1) mod 4, game.py:92
+    sn.last = dir;
+    int y = sn.head / SIDE, x = sn.head - y * SIDE;
+    y += (dir == 0) ? -1 : (dir == 2) ? 1 : 0;                // 0 up, 1 right, 2 down, 3 left (game.py:330-342)
+    x += (dir == 1) ? 1 : (dir == 3) ? -1 : 0;
+    off = ((unsigned)y >= (unsigned)SIDE) || ((unsigned)x >= (unsigned)SIDE);
+    nh = off ? -1 : y * SIDE + x;
+    sn.health -= health_dec;
+  }
+  // 3. eat, first come in list order (game.py:121-127)
+  const bool onfood = was_alive && !off && sb[nh < 0 ? 0 : nh] == kFood;
+  bool earlier = false, shared = false, lose = false;
+  unsigned blocked = 0;   // head cells among this lane's cells (for the spawn's empty set)
+#pragma unroll
+  for (int s2 = 0; s2 < kMaxSnakes; ++s2) {
+    const int nh2 = __shfl_sync(kFull, nh, s2);
+    const int al2 = __shfl_sync(kFull, (int)was_alive, s2);
+    if (al2 && nh2 >= 0) {
+      if (nh2 == nh && s2 < lane) earlier = true;
+      if (nh2 / CPL == lane) blocked |= 1u << (nh2 - lane * CPL);
+    }
+  }
+  const bool eat = onfood && !earlier;
+  const unsigned ate_mask = __ballot_sync(kFull, eat);
+  if (eat) { sb[nh] = 0; sn.health = 100; sn.len += 1; }       // Snake.grow, game.py:360-365
+  m.eaten += (uint32_t)__popc(ate_mask);
+  __syncwarp();
+  // every stamp ages by one; growers get it back (tail duplicated); a stamp reaching 0 vacates the cell
+  int n_food = 0, n_empty = 0;
+  unsigned empty_bits = 0;
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane * CPL + q;
+    uint32_t v = sb[c];
+    if (cell_is_body(v)) {
+      const int o = cell_owner(v);
+      int d = cell_dist(v) - 1;
+      if (d == 0) v = 0;
+      else { if ((ate_mask >> o) & 1u) d += 1; v = (uint32_t)((o << 12) | d); }
+      sb[c] = (uint16_t)v;
+    }
+    n_food += (v == kFood);
+    if (v == 0 && c < CELLS && !((blocked >> q) & 1u)) { n_empty += 1; empty_bits |= 1u << q; }
+  }
+  __syncwarp();
+  // 4. spawn (game.py:130-138): before the kill decision, so about-to-die snakes still block their cells
+  if (spawn_mode == 1) {
+    if (lane == 0 && spawn_cell >= 0) sb[spawn_cell] = kFood;
+    __syncwarp();
+  } else if (spawn_mode == 2) {
+    uint32_t r[4];
+    philox4x32_10(game_id, m.episode, RS_SPAWN, m.turn, seed, r);
+    const int tot_food = warp_sum_i32(n_food);
+    if (tot_food == 0 || r[0] <= chance_thresh) {
+      const int pre = warp_excl_scan_i32(n_empty, lane);
+      const int tot_empty = __shfl_sync(kFull, pre + n_empty, 31);
+      if (tot_empty > 0) {
+        int k = (int)mulhi32(r[1], (uint32_t)tot_empty) - pre;
+        if (k >= 0 && k < n_empty) {
+#pragma unroll
+          for (int q = 0; q < CPL; ++q)
+            if ((empty_bits >> q) & 1u) { if (k == 0) sb[lane * CPL + q] = kFood; --k; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // 5. kill decision (game.py:144-165): wall > body > head-on > starvation, first matching rule only
+  int cause = 0;
+  if (was_alive) {
+    if (off) cause = 1;
+    else if (cell_is_body(sb[nh])) cause = 2;
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < kMaxSnakes; ++s2) {
+    const int nh2 = __shfl_sync(kFull, nh, s2);
+    const int al2 = __shfl_sync(kFull, (int)was_alive, s2);
+    const int len2 = __shfl_sync(kFull, sn.len, s2);
+    if (was_alive && !off && al2 && s2 != lane && nh2 == nh) { shared = true; if (sn.len <= len2) lose = true; }
+  }
+  if (was_alive && cause == 0) {
+    if (shared) { if (lose) cause = 3; }
+    else if (sn.health <= 0) cause = 4;
+  }
+  m.wall += (uint32_t)__popc(__ballot_sync(kFull, cause == 1));
+  m.body += (uint32_t)__popc(__ballot_sync(kFull, cause == 2));
+  m.headc += (uint32_t)__popc(__ballot_sync(kFull, cause == 3));
+  m.starve += (uint32_t)__popc(__ballot_sync(kFull, cause == 4));
+  const unsigned dead_mask = __ballot_sync(kFull, cause != 0);
+  // 6. remove (game.py:167-192): the dead snake's stamps are cleared, its head was never stamped
+  if (dead_mask) {
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const uint32_t v = sb[lane * CPL + q];
+      if (cell_is_body(v) && ((dead_mask >> cell_owner(v)) & 1u)) sb[lane * CPL + q] = 0;
+    }
+    __syncwarp();
+  }
+  if (cause != 0) { sn.alive = 0; sn.reward = 2; sn.head = 0xFFFF; sn.len = 0; sn.health = 0; }
+  else if (was_alive) { sb[nh] = (uint16_t)((lane << 12) | sn.len); sn.head = nh; }
+  __syncwarp();
+  // 7. terminate (game.py:197-205)
+  m.turn += 1;
+  TicResult r;
+  r.live_mask = __ballot_sync(kFull, sn.alive != 0);
+  r.dead_mask = dead_mask;
+  r.ended = __popc(r.live_mask) <= 1;
+  if (r.ended) { m.flags |= 1u; if (sn.alive) sn.reward = 1; }
+  return r;
+}
+
+// ---- Game.make_state (game.py:215-257) ---------------------------------------------------------------------------
+// Per-game, viewer independent part, computed once from this lane's cells:
+//   f1   = ch1 value  dist*0.02 in double, rounded once to float (game.py:239,257)
+//   hs   = id of the snake whose head is on the cell, or -1 (the head is the stamp with dist == length)
+//   food = cell holds food
+template <class G>
+struct CellView {
+  float f1[G::CPL];
+  int8_t hs[G::CPL];
+  bool food[G::CPL];
+};
+template <class G>
+__device__ __forceinline__ void warp_cell_view(const uint16_t* sb, const Snake& sn, CellView<G>& cv) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int q = 0; q < G::CPL; ++q) {
+    const uint32_t v = sb[lane * G::CPL + q];
+    const bool body = cell_is_body(v);
+    const int o = body ? cell_owner(v) : 0;
+    const int len_o = __shfl_sync(kFull, sn.len, o);
+    const int d = cell_dist(v);
+    cv.f1[q] = body ? (float)((double)d * 0.02) : 0.0f;
+    cv.hs[q] = (int8_t)((body && d == len_o) ? o : -1);
+    cv.food[q] = (v == kFood);
+  }
+}
+
+// Encode the plane of viewer `vs` (warp-uniform snake id).  Cell-centric: the staging buffer is filled with the wall
+// background [0,1,0] (game.py:219), then each lane scatters its CPL board cells to their rotated, recentred pixel
+// (game.py:247-257), then the warp streams the plane to HBM with 16-byte stores.  `stage` holds the plane at float
+// offset a = (gidx0 & 3) so that shared and global addresses share their 16-byte phase.
+// gidx0 = float index of the plane's first element in the output buffer (planes are only 4-byte aligned: 1323 floats).
+// When out == nullptr nothing is written (key only).  When key != nullptr the 128-bit plane key is accumulated.
+template <class G, bool kWantKey>
+__device__ __forceinline__ void warp_encode(const CellView<G>& cv, const Snake& sn, int vs, float* stage, float* out,
+                                            size_t gidx0, uint64_t* key0, uint64_t* key1) {
+  constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS, N = G::N, PLANE = G::PLANE;
+  const int lane = lane_id();
+  const int vhead = __shfl_sync(kFull, sn.head, vs);
+  const int vlen = __shfl_sync(kFull, sn.len, vs);
+  const int vhp = __shfl_sync(kFull, sn.health, vs);
+  const int vrot = __shfl_sync(kFull, sn.last, vs);
+  const int hy = vhead / SIDE, hx = vhead - hy * SIDE;
+  // ch0 of a head of snake `lane` as seen by the viewer (game.py:229,232), ch2 of food (game.py:244): double math
+  const float my_hv = (float)(((double)sn.len - ((double)vlen - 0.5)) * 0.04);
+  const float foodv = (float)((double)(101 - vhp) * 0.01);
+  const int a = (int)(gidx0 & 3);
+  if (out != nullptr) {
+    // background: element e of the plane is 1.0 iff e % 3 == 1; stage index = a + e
+    for (int q4 = lane; q4 < G::STAGE / 4; q4 += 32) {
+      const int e0 = q4 * 4 - a;               // may be negative for the first vector: harmless filler
+      const int r = ((e0 % 3) + 3) % 3;
+      float4 v;
+      v.x = (r == 1) ? 1.0f : 0.0f; v.y = (r == 0) ? 1.0f : 0.0f; v.z = (r == 2) ? 1.0f : 0.0f; v.w = v.x;
+      reinterpret_cast<float4*>(stage)[q4] = v;
+    }
+    __syncwarp();
+  }
+  uint64_t k0 = 0, k1 = 0;
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane * CPL + q;
+    const int hsq = cv.hs[q];
+    const float hv = __shfl_sync(kFull, my_hv, hsq < 0 ? 0 : hsq);
+    if (c < CELLS) {
+      const int y = c / SIDE, x = c - y * SIDE;
+      const int gy = y - hy + (SIDE - 1), gx = x - hx + (SIDE - 1);       // game.py:249-251
+      int i, j;                                                           // numpy.rot90(grid, k), game.py:257
+      if (vrot == 0) { i = gy; j = gx; }
+      else if (vrot == 1) { i = N - 1 - gx; j = gy; }
+      else if (vrot == 2) { i = N - 1 - gy; j = N - 1 - gx; }
+      else { i = gx; j = N - 1 - gy; }
+      const int p = i * N + j;
+      float t0, t1, t2;
+      if (c == vhead) { t0 = t1 = t2 = -1.0f; }                           // game.py:248
+      else { t0 = (hsq >= 0) ? hv : 0.0f; t1 = cv.f1[q]; t2 = cv.food[q] ? foodv : 0.0f; }
+      if (out != nullptr) { float* d = stage + a + 3 * p; d[0] = t0; d[1] = t1; d[2] = t2; }
+      if (kWantKey) key_accumulate((uint32_t)p, __float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), k0, k1);
+    }
+  }
+  if (kWantKey) {
+    k0 = warp_sum_u64(k0); k1 = warp_sum_u64(k1);
+    if (k0 == 0) k0 = 1;
+    *key0 = k0; *key1 = k1;
+  }
+  if (out != nullptr) {
+    __syncwarp();
+    const size_t gbase = gidx0 - (size_t)a;                 // 16-byte aligned float index (buffer base is aligned)
+    const size_t gA = (gidx0 + 3) & ~(size_t)3, gend = gidx0 + PLANE, gE = gend & ~(size_t)3;
+    const int nvec = (int)((gE - gA) >> 2), v0 = (int)((gA - gbase) >> 2);
+    const float4* s4 = reinterpret_cast<const float4*>(stage) + v0;
+    float4* o4 = reinterpret_cast<float4*>(out + gA);
+    for (int v = lane; v < nvec; v += 32) st_stream_f4(o4 + v, s4[v]);
+    const int nhead = (int)(gA - gidx0), ntail = (int)(gend - gE);
+    if (lane < nhead) out[gidx0 + lane] = stage[a + lane];
+    if (lane < ntail) out[gE + lane] = stage[(int)(gE - gbase) + lane];
+    __syncwarp();                                            // stage is reused by the next plane
+  }
+}
+
+}  // namespace asz

@@ -1,0 +1,130 @@
+"""Python handle on one device-resident engine (include/asz_b200.h).  PyTorch is used only for device memory and
+streams; all game, encode and search work happens in libasz_b200.so."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (SPAWN_NATIVE, SPAWN_NONE, SPAWN_REPLAY, STEP_AUTO_RESET, STEP_ENCODE, STEP_KEYS, STEP_RANDOM_ACT,
+                   STEP_TIC, AszError, check)
+
+__all__ = ["Engine", "AszError", "STEP_TIC", "STEP_ENCODE", "STEP_AUTO_RESET", "STEP_RANDOM_ACT", "STEP_KEYS",
+           "SPAWN_NONE", "SPAWN_REPLAY", "SPAWN_NATIVE"]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, side=11, snakes=4, health_dec=1, food_chance=0.15, games=1, seed=0, max_depth=0, max_breadth=0,
+                 softmax_base=100.0, training=False, table_log2=0, numpy1_mask=False, device=None):
+        if not torch.cuda.is_available():
+            raise AszError("no CUDA device: alphasnake_zero_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.L = _lib.lib()
+        self.side, self.S, self.G = side, snakes, games
+        self.N = 2 * side - 1
+        self.plane = self.N * self.N * 3
+        cfg = _lib.Config(side, snakes, health_dec, food_chance, games, seed, max_depth, max_breadth, softmax_base,
+                          int(training), table_log2, int(numpy1_mask))
+        self.cfg = cfg
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.L.asz_engine_create(C.byref(h), C.byref(cfg)))
+        self.h = h
+        dev = self.device
+        self.max_rows = games * snakes
+        self._planes = None
+        self.row_ids = torch.zeros(self.max_rows, dtype=torch.int32, device=dev)
+        self.row_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ended = torch.zeros(games, dtype=torch.uint8, device=dev)
+        self.rewards = torch.zeros(games, 8, dtype=torch.int8, device=dev)
+        self.keys = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.asz_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def planes(self):
+        """[G*S, N, N, 3] float32 batch buffer (allocated on first use)."""
+        if self._planes is None:
+            self._planes = torch.empty(self.max_rows, self.N, self.N, 3, dtype=torch.float32, device=self.device)
+        return self._planes
+
+    def reset(self):
+        check(self.L.asz_reset(self.h, self.stream))
+
+    # ---- state interchange -------------------------------------------------------------------------------------
+    def get_state(self, game):
+        Cn = self.side * self.side
+        snake = np.zeros((self.S, 6), np.int32); owner = np.zeros(Cn, np.int32); dist = np.zeros(Cn, np.int32)
+        food = np.zeros(Cn, np.int32); counters = np.zeros(8, np.int32)
+        check(self.L.asz_get_state(self.h, game, _np(snake), _np(owner), _np(dist), _np(food), _np(counters)))
+        return dict(snake=snake, owner=owner, dist=dist, food=food, counters=counters)
+
+    def set_state(self, game, d):
+        a = {k: np.ascontiguousarray(d[k], dtype=np.int32) for k in ("snake", "owner", "dist", "food")}
+        cnt = np.zeros(8, np.int32)
+        c = np.asarray(d["counters"]).astype(np.int32)
+        cnt[:6] = c[:6]
+        cnt[6] = 0
+        cnt[7] = 0
+        check(self.L.asz_set_state(self.h, game, _np(a["snake"]), _np(a["owner"]), _np(a["dist"]), _np(a["food"]), _np(cnt)))
+
+    # ---- lockstep step -----------------------------------------------------------------------------------------
+    def step(self, actions=None, spawn_cells=None, spawn_mode=SPAWN_NATIVE, tic=True, encode=True, auto_reset=False,
+             random_actions=False, keys=False, planes=None):
+        """One fused launch.  actions: uint8 cuda tensor [G, 8]; spawn_cells: int32 cuda tensor [G].
+        Returns nothing; results are in self.row_count / row_ids / planes / ended / rewards (device tensors)."""
+        flags = (STEP_TIC if tic else 0) | (STEP_ENCODE if encode else 0) | (STEP_AUTO_RESET if auto_reset else 0) | \
+                (STEP_RANDOM_ACT if random_actions else 0) | (STEP_KEYS if keys else 0)
+        a = _lib.StepArgs()
+        a.flags = flags
+        a.spawn_mode = spawn_mode
+        a.d_actions = actions.data_ptr() if actions is not None else None
+        a.d_spawn_cells = spawn_cells.data_ptr() if spawn_cells is not None else None
+        if encode:
+            pl = self.planes if planes is None else planes
+            a.d_planes = pl.data_ptr()
+            a.max_rows = pl.shape[0]
+        a.d_row_ids = self.row_ids.data_ptr()
+        if keys:
+            if self.keys is None:
+                self.keys = torch.zeros(self.max_rows, 2, dtype=torch.int64, device=self.device)
+            a.d_keys = self.keys.data_ptr()
+        a.d_row_count = self.row_count.data_ptr()
+        a.d_ended = self.ended.data_ptr()
+        a.d_rewards = self.rewards.data_ptr()
+        check(self.L.asz_env_step(self.h, C.byref(a), self.stream))
+
+    def totals(self):
+        t = np.zeros(16, np.uint64)
+        check(self.L.asz_get_totals(self.h, _np(t)))
+        return dict(zip(("wall", "body", "head", "starve", "food_eaten", "game_length", "episodes", "tics", "planes"),
+                        t.tolist()))
+
+    # ---- convenience used by tests and the drop-in classes -------------------------------------------------------
+    def rows(self):
+        """(row_ids numpy [n], planes torch view [n, N, N, 3]) of the last encode, sorted by (game, snake)."""
+        n = int(self.row_count.item())
+        ids = self.row_ids[:n]
+        order = torch.argsort(ids)
+        return ids[order].cpu().numpy(), self.planes[:n][order]

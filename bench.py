@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 self-play engine.
+
+Workload at N=1 (BASELINE.json configs[1]): 65,536 lockstep 11x11 4-snake games, uniform-random joint actions,
+native food spawn, in-place reset of finished games, every live snake's fp32 NHWC plane encoded every tic.
+A "step" is one lockstep tic of all games = one launch of the fused tic+encode kernel.  N>1: one process per GPU
+(torchrun), every rank steps its own 65,536 games (weak scaling, no collective on the data path).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of every field.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIDE, SNAKES, HEALTH_DEC, CHANCE, GAMES = 11, 4, 1, 0.15, 65536
+PLANE_BYTES = 21 * 21 * 3 * 4          # 5,292 B
+STATE_BYTES = 128                      # nominal compact record, read + write => 2x
+METRIC, UNIT = "env_steps_per_sec", "env steps/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(target_s=12.0):
+    """The CPU oracle (C restatement of the reference, kind "port") on the same workload, all host threads, on a
+    bounded sample sized for ~target_s seconds."""
+    from oracle import oracle as orc
+    orc.build()
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    orc.env_run(2048, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, 20, encode=True, n_threads=cores)
+    rate = 2048 * 20 / max(time.time() - t0, 1e-6)
+    tics = 100
+    g = int(max(2048, min(GAMES, rate * target_s / tics)))
+    t0 = time.time()
+    st = orc.env_run(g, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, tics, encode=True, n_threads=cores)
+    dt = time.time() - t0
+    return {"value": st["steps"] / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d games x %d tics (tic + encode of every live snake, %.2f planes/step), C oracle, %d threads, %.1f s"
+                      % (g, tics, st["planes"] / st["steps"], cores, dt)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    cores = os.cpu_count() or 1
+    g = 8192
+    games = []
+    for gi in range(g):
+        og = orc.OracleGame(SIDE, SIDE, SNAKES, HEALTH_DEC)
+        og.init_native(0, gi, 0)
+        games.append(og)
+    for _ in range(args.warmup):
+        orc.env_run(g, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, 1, encode=True, n_threads=cores, games=games)
+    t0 = time.time()
+    steps = planes = 0
+    for _ in range(args.steps):
+        st = orc.env_run(g, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, 1, encode=True, n_threads=cores, games=games)
+        steps += st["steps"]; planes += st["planes"]
+    dt = time.time() - t0
+    v = steps / dt
+    sample = "%d of the %d games per step, all %d host threads, C port of the reference (oracle/asz_oracle.c)" % (g, GAMES, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16/f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 11x11, 4 snakes, lockstep games, uniform-random actions, tic + fp32 plane encode",
+                   "games_per_step": g, "planes_per_step": planes / max(steps, 1)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from alphasnake_zero_b200 import _lib
+    from alphasnake_zero_b200.engine import Engine
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    eng = Engine(side=SIDE, snakes=SNAKES, health_dec=HEALTH_DEC, food_chance=CHANCE, games=GAMES, seed=1000 + rank)
+    eng.reset()
+    _ = eng.planes
+    kw = dict(spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=True, auto_reset=True, random_actions=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident throughput ("value") and the kernel roofline -----------------------------------
+    for _ in range(W):
+        eng.step(**kw)
+    barrier()
+    t_before = eng.totals()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        eng.step(**kw)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    t_after = eng.totals()
+    steps_local = t_after["tics"] - t_before["tics"]
+    planes_local = t_after["planes"] - t_before["planes"]
+
+    # ---- leg 2: end to end through the C ABI with HOST buffers -----------------------------------------------------
+    rng = np.random.default_rng(rank)
+    n_pool = 8
+    act_pool = [torch.from_numpy(rng.integers(0, 3, size=(GAMES, 8), dtype=np.uint8)).pin_memory() for _ in range(n_pool)]
+    h_ended = torch.zeros(GAMES, dtype=torch.uint8).pin_memory()
+    h_rewards = torch.zeros(GAMES, 8, dtype=torch.int8).pin_memory()
+    rows = C.c_int32(0)
+    L = _lib.lib()
+    flags = _lib.STEP_TIC | _lib.STEP_ENCODE | _lib.STEP_AUTO_RESET
+
+    def e2e_step(i):
+        _lib.check(L.asz_env_step_host(eng.h, flags, _lib.SPAWN_NATIVE, C.c_void_p(act_pool[i % n_pool].data_ptr()), None,
+                                       C.c_void_p(h_ended.data_ptr()), C.c_void_p(h_rewards.data_ptr()), C.byref(rows),
+                                       None, None, eng.stream))
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_b = eng.totals()
+    barrier()
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_steps_local = eng.totals()["tics"] - t_b["tics"]
+
+    # ---- reduce over ranks: max time, sum of work ----------------------------------------------------------------
+    vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_ms = float(mx[0]), float(mx[1])
+        steps_all, planes_all, e2e_steps_all = float(sm[2]), float(sm[3]), float(sm[4])
+    else:
+        steps_all, planes_all, e2e_steps_all = float(steps_local), float(planes_local), float(e2e_steps_local)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = steps_all / (ms * 1e-3)
+    peak, peak_src = peaks()
+    # roofline of the dominant (only) kernel: algorithmic bytes per launch on THIS rank / average launch duration
+    bytes_per_launch = (planes_local * PLANE_BYTES + steps_local * 2 * STATE_BYTES) / K
+    launch_s = (ev0.elapsed_time(ev1) * 1e-3) / K
+    achieved = bytes_per_launch / launch_s / 1e9
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get("env_step_kernel_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16/f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: %d lockstep 11x11 4-snake games per GPU, uniform-random joint actions (in-kernel Philox), "
+                               "native food spawn, in-place reset, tic + fp32 NHWC plane encode of every live snake" % GAMES,
+                   "games_per_gpu": GAMES, "planes_per_step": planes_all / max(steps_all, 1),
+                   "l2": "each launch writes %.0f MB of planes (> 126 MB L2); the 21 MB of game records may stay L2 resident"
+                         % (bytes_per_launch / 1e6)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "env_step_kernel<11,8>", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_per_launch},
+        "e2e": {"value": e2e_steps_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": GAMES * 8,
+                "d2h_bytes_per_step": GAMES + GAMES * 8 + 4,
+                "note": "asz_env_step_host: pinned host actions in, per-game ended/rewards + row count out; planes stay in HBM for the network"},
+        "gpu_launches": K, "clocks": clocks,
+    }
+    if world == 1:
+        out["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

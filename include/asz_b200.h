@@ -1,0 +1,134 @@
+/*
+ * asz_b200.h -- C ABI of the B200-native AlphaSnake-Zero self-play engine (libasz_b200.so).
+ *
+ * The reference (Fool-Yang/AlphaSnake-Zero) is pure Python and has no FFI of its own; the seams this library sits
+ * behind are the duck-typed Python classes of code/utils/ (SURVEY.md section 8(b)).  Every entry point below names
+ * the reference interface it replaces (file:line under /root/reference/code/utils/).  The Python mirror of those
+ * classes lives in alphasnake_zero_b200/utils/ and binds this header with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative asz_status, asz_last_error() explains;
+ *   - pointers named d_* are DEVICE pointers (e.g. torch tensor .data_ptr()), h_* are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls only enqueue work on
+ *     that stream unless documented as synchronous (the *_host / readback calls);
+ *   - one engine per GPU (the device current at asz_engine_create), calls on one engine are not thread-safe
+ *     (the reference is single-threaded);
+ *   - snakes are indexed by id (0..S-1), slot = game*8 + snake in per-snake arrays (8 = ASZ_MAX_SNAKES);
+ *   - relative moves are 0 = left, 1 = straight, 2 = right (game.py:92).
+ */
+#ifndef ASZ_B200_H
+#define ASZ_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASZ_MAX_SNAKES 8
+#define ASZ_VERSION 1
+
+typedef enum {
+  ASZ_OK = 0,
+  ASZ_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+  ASZ_ERR_CUDA = -2,     /* a CUDA runtime call failed */
+  ASZ_ERR_STATE = -3,    /* call not valid in the engine's current state */
+  ASZ_ERR_CAPACITY = -4  /* an output or table capacity was exceeded */
+} asz_status;
+
+/* Engine configuration.  Mirrors the constructor arguments of Game / MPGameRunner (game.py:13, mp_game_runner.py:7)
+ * and Agent (agent.py:9-10). */
+typedef struct {
+  int32_t side;            /* board height == width: 7, 11 or 19 (the standard boards of game.py:22-28) */
+  int32_t snakes;          /* S, 1..8 (game.py:25-29 samples S of 8 start cells) */
+  int32_t health_dec;      /* game.py:13 health_dec */
+  float food_chance;       /* game.py:13 food_spawn_chance (0.15 in the reference's runners) */
+  int32_t games;           /* G, number of root games held by this engine (mp_game_runner.py:13) */
+  uint64_t seed;           /* key of the engine's counter-based RNG (Philox4x32-10) */
+  /* search (0 disables the search subsystem and its allocations) */
+  int32_t max_depth;       /* agent.py:10 max_MCTS_depth */
+  int32_t max_breadth;     /* agent.py:10 max_MCTS_breadth */
+  float softmax_base;      /* agent.py:9 softmax_base */
+  int32_t training;        /* agent.py:9 training */
+  int32_t table_log2;      /* log2 of the Q-table capacity in slots (0 = choose from G, breadth, depth) */
+  int32_t numpy1_mask;     /* 0: obstacle threshold compared in float32 (NumPy >= 2), 1: in float64 (NumPy 1.18),
+                              alpha_nnet.py:75-76, SURVEY.md D-11 */
+} asz_config;
+
+typedef struct asz_engine asz_engine;
+
+const char* asz_last_error(void);
+int asz_version(void);
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+/* MPGameRunner.__init__ (mp_game_runner.py:7-20): allocates G games on the current device; games are NOT initialised
+ * until asz_reset / asz_set_state. */
+int asz_engine_create(asz_engine** out, const asz_config* cfg);
+int asz_engine_destroy(asz_engine* e);
+/* Game.__init__ for every game (game.py:13-61) with the engine's RNG; episode counters restart at 0. */
+int asz_reset(asz_engine* e, void* stream);
+
+/* ---- state interchange (debug / replay / tests); synchronous; all HOST int32 arrays --------------------------
+ * canonical dump of one game:
+ *   snake[S*6]   = alive, health, length, last_move, head_cell (-1 none), reward (0 none, 1, -1)
+ *   owner[side^2] (-1 none), dist[side^2] (distance from tail of the topmost segment, 0 none), food[side^2] (0/1)
+ *   counters[8]  = wall, body, head, starve, food_eaten, game_length, episode, done
+ * Replaces direct attribute access on Game objects (game.snakes, game.food, game.rewards, counters; game.py:20-61). */
+int asz_get_state(asz_engine* e, int32_t game, int32_t* h_snake, int32_t* h_owner, int32_t* h_dist, int32_t* h_food,
+                  int32_t* h_counters);
+int asz_set_state(asz_engine* e, int32_t game, const int32_t* h_snake, const int32_t* h_owner, const int32_t* h_dist,
+                  const int32_t* h_food, const int32_t* h_counters);
+
+/* ---- lockstep tic + fused plane encode (Game.tic game.py:87-205, Game.get_states game.py:68-69, 215-257) ------
+ * flags */
+#define ASZ_STEP_TIC 1u          /* advance every live game by one tic */
+#define ASZ_STEP_ENCODE 2u       /* write the plane of every live snake (after the tic) into d_planes */
+#define ASZ_STEP_AUTO_RESET 4u   /* a game that ends is re-initialised in the same launch (its final rewards and
+                                    counters are reported first); config-2 workload of BASELINE.json */
+#define ASZ_STEP_RANDOM_ACT 8u   /* ignore d_actions, draw uniform relative moves from the engine RNG */
+#define ASZ_STEP_KEYS 16u        /* also write the 128-bit plane key of every row into d_keys */
+/* spawn modes */
+#define ASZ_SPAWN_NONE 0         /* never spawn (Game.subgame, game.py:268) */
+#define ASZ_SPAWN_REPLAY 1       /* d_spawn_cells[g] = cell index of the food spawned this tic, or -1 (trace replay) */
+#define ASZ_SPAWN_NATIVE 2       /* engine RNG: coin `random() <= chance` or board without food, uniform empty cell */
+
+typedef struct {
+  uint32_t flags;
+  int32_t spawn_mode;
+  const uint8_t* d_actions;      /* [G*8] relative move per (game, snake id); read where the snake is alive */
+  const int32_t* d_spawn_cells;  /* [G] for ASZ_SPAWN_REPLAY */
+  float* d_planes;               /* [max_rows][2*side-1][2*side-1][3] float32 NHWC, rows compacted; 16-byte aligned */
+  int32_t* d_row_ids;            /* [max_rows] game*8 + snake of every row written */
+  uint64_t* d_keys;              /* [max_rows*2] when ASZ_STEP_KEYS */
+  int32_t max_rows;
+  int32_t* d_row_count;          /* [1] number of rows written by this call (the call zeroes it first) */
+  uint8_t* d_ended;              /* [G] 1 when the game ended in this tic (may be NULL) */
+  int8_t* d_rewards;             /* [G*8] final rewards of games that ended in this tic: 0 none, 1, -1 (may be NULL) */
+} asz_step_args;
+
+/* Enqueues one fused launch.  Row order inside d_planes is unspecified across games (rows of one game are
+ * contiguous and in ascending snake id, the reference's live-list order, game.py:69); d_row_ids identifies them. */
+int asz_env_step(asz_engine* e, const asz_step_args* args, void* stream);
+
+/* Host-buffer convenience wrapper used for end-to-end timing: copies h_actions (pinned, [G*8]) to the device, runs
+ * asz_env_step into the engine's internal plane buffer, copies the per-game results back and synchronises.
+ * h_ended [G], h_rewards [G*8], h_row_count [1]; h_planes may be NULL (planes stay device resident for the network)
+ * or a pinned buffer that receives rows*plane floats. */
+int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
+                      const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, int32_t* h_row_count,
+                      float* h_planes, int32_t* h_row_ids, void* stream);
+
+/* Running totals over games that ended since the last asz_reset (mp_game_runner.py:56-61, 71-76 divides by G):
+ * h_totals[16] = wall, body, head, starve, food_eaten, game_length, episodes_finished, tics_executed, planes_written,
+ * then 7 reserved slots.  Synchronous. */
+int asz_get_totals(asz_engine* e, uint64_t* h_totals);
+
+/* device pointer of the engine's internal plane buffer (capacity G*S rows) and row-id buffer */
+float* asz_internal_planes(asz_engine* e);
+int32_t* asz_internal_row_ids(asz_engine* e);
+size_t asz_plane_floats(const asz_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASZ_B200_H */

@@ -1,0 +1,210 @@
+"""GPU parity: the CUDA lockstep tic + fused plane encode (through the C ABI) against
+ (1) the fixtures produced by the unmodified reference, (2) the CPU oracle on seeded full-size runs."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import assert_dump_equal, digest, golden_dump, load
+
+pytestmark = pytest.mark.gpu
+
+ENVS = ["11x11x4", "11x11x4_dec9", "7x7x4", "19x19x8", "11x11x2", "7x7x8"]
+
+
+def _engine(**kw):
+    from alphasnake_zero_b200.engine import Engine
+    return Engine(**kw)
+
+
+def init_dump(side, S, start, last, food):
+    Cn = side * side
+    snake = np.zeros((S, 6), np.int32); owner = np.full(Cn, -1, np.int32); dist = np.zeros(Cn, np.int32)
+    fd = np.zeros(Cn, np.int32)
+    for i in range(S):
+        c = int(start[i][0]) * side + int(start[i][1])
+        snake[i] = [1, 100, 3, int(last[i]), c, 0]
+        owner[c] = i; dist[c] = 3
+    for (y, x) in food:
+        fd[int(y) * side + int(x)] = 1
+    return dict(snake=snake, owner=owner, dist=dist, food=fd, counters=np.zeros(8, np.int32))
+
+
+@pytest.mark.parametrize("name", ENVS)
+def test_env_replay_against_reference(name):
+    import torch
+    z = load("env_%s.npz" % name)
+    side, S, dec = int(z["H"]), int(z["S"]), int(z["health_dec"])
+    gp = z["game_ptr"]
+    G = len(gp) - 1
+    eng = _engine(side=side, snakes=S, health_dec=dec, games=G, seed=1)
+    for gi in range(G):
+        nf = int(z["init_nfood"][gi])
+        eng.set_state(gi, init_dump(side, S, z["init_start"][gi], z["init_last"][gi], z["init_food"][gi][:nf]))
+    live_ids = [list(range(S)) for _ in range(G)]
+    full = {(int(t), int(k)): i for i, (t, k) in enumerate(z["full_idx"])}
+    max_len = int((gp[1:] - gp[:-1]).max())
+    n_planes = 0
+    for step in range(max_len):
+        actions = np.ones((G, 8), np.uint8)
+        spawn = np.full(G, -1, np.int32)
+        running = []
+        for gi in range(G):
+            t = int(gp[gi]) + step
+            if t >= int(gp[gi + 1]):
+                continue
+            running.append(gi)
+            n = int(z["nlive"][t])
+            assert n == len(live_ids[gi])
+            for k, sid in enumerate(live_ids[gi]):
+                actions[gi, sid] = z["moves"][t][k]
+            spawn[gi] = int(z["spawn"][t])
+        eng.step(actions=torch.from_numpy(actions).cuda(), spawn_cells=torch.from_numpy(spawn).cuda(), spawn_mode=1,
+                 tic=True, encode=True)
+        ids, planes = eng.rows()
+        planes = planes.cpu().numpy()
+        ended = eng.ended.cpu().numpy()
+        row_of = {int(i): r for r, i in enumerate(ids)}
+        for gi in running:
+            t = int(gp[gi]) + step
+            want = golden_dump(z, t)
+            assert_dump_equal(eng.get_state(gi), want, "%s game %d tic %d" % (name, gi, t))
+            assert int(ended[gi]) == int(z["ended"][t])
+            live_ids[gi] = [s for s in range(S) if want["snake"][s][0] == 1]
+            d0, d1 = int(z["dig_ptr"][t]), int(z["dig_ptr"][t + 1])
+            if z["ended"][t]:
+                assert all((gi * 8 + s) not in row_of for s in range(S))   # ended games produce no rows
+                continue
+            assert d1 - d0 == len(live_ids[gi])
+            for k, sid in enumerate(live_ids[gi]):
+                p = planes[row_of[gi * 8 + sid]]
+                assert digest(p) == z["digests"][d0 + k], (name, gi, t, k)
+                if (t, k) in full:
+                    assert np.array_equal(p.view(np.uint32), z["full_planes"][full[(t, k)]].view(np.uint32))
+                n_planes += 1
+        # finished games must not change any more and must not emit rows
+        assert len(ids) == sum(len(live_ids[g]) for g in running if not z["ended"][int(gp[g]) + step])
+    assert n_planes > 0
+    eng.close()
+
+
+def test_edge_cases_against_reference():
+    import torch
+    z = load("edge_cases.npz")
+    n = len(z["names"])
+    for dec in sorted(set(z["health_dec"].tolist())):
+        idx = [i for i in range(n) if int(z["health_dec"][i]) == dec]
+        eng = _engine(side=11, snakes=4, health_dec=dec, games=len(idx), seed=0)
+        for j, i in enumerate(idx):
+            eng.set_state(j, {k: z["before_" + k][i] for k in ("snake", "owner", "dist", "food", "counters")})
+        # planes of the hand-built states
+        eng.step(tic=False, encode=True)
+        ids, planes = eng.rows()
+        planes = planes.cpu().numpy()
+        row_of = {int(v): r for r, v in enumerate(ids)}
+        for j, i in enumerate(idx):
+            pb = z["planes_before"][int(z["pb_ptr"][i]):int(z["pb_ptr"][i + 1])]
+            live = [s for s in range(4) if z["before_snake"][i][s][0] == 1]
+            assert len(pb) == len(live)
+            for k, sid in enumerate(live):
+                assert np.array_equal(planes[row_of[j * 8 + sid]].view(np.uint32), pb[k].view(np.uint32)), z["names"][i]
+        actions = np.ones((len(idx), 8), np.uint8)
+        for j, i in enumerate(idx):
+            live = [s for s in range(4) if z["before_snake"][i][s][0] == 1]
+            for k, sid in enumerate(live):
+                actions[j, sid] = z["moves"][i][k]
+        eng.step(actions=torch.from_numpy(actions).cuda(), spawn_mode=0, tic=True, encode=True)
+        ids, planes = eng.rows()
+        planes = planes.cpu().numpy()
+        row_of = {int(v): r for r, v in enumerate(ids)}
+        ended = eng.ended.cpu().numpy()
+        for j, i in enumerate(idx):
+            name = str(z["names"][i])
+            after = {k: z["after_" + k][i] for k in ("snake", "owner", "dist", "food", "counters")}
+            assert_dump_equal(eng.get_state(j), after, name)
+            assert int(ended[j]) == int(z["ended"][i]), name
+            if z["ended"][i]:
+                continue
+            pa = z["planes_after"][int(z["pa_ptr"][i]):int(z["pa_ptr"][i + 1])]
+            live = [s for s in range(4) if after["snake"][s][0] == 1]
+            for k, sid in enumerate(live):
+                assert np.array_equal(planes[row_of[j * 8 + sid]].view(np.uint32), pa[k].view(np.uint32)), name
+        eng.close()
+
+
+@pytest.mark.parametrize("side,S,dec,G,tics", [(11, 4, 1, 4096, 120), (7, 4, 9, 1024, 80), (19, 8, 1, 512, 150),
+                                               (11, 2, 3, 1000, 60), (7, 8, 1, 333, 60)])
+def test_native_run_against_oracle(side, S, dec, G, tics):
+    """Seeded native runs (engine RNG for layouts, actions and food; auto reset): every game's final state, the
+    totals and an order-free checksum over every plane written must equal the oracle's, bit for bit."""
+    import torch
+    from oracle import oracle as orc
+    seed = 1234 + side
+    eng = _engine(side=side, snakes=S, health_dec=dec, games=G, seed=seed)
+    eng.reset()
+    csum = torch.zeros((), dtype=torch.int64, device="cuda")
+    planes = 0
+    # initial planes are not part of the oracle's env_run accounting (it encodes after every tic)
+    for _ in range(tics):
+        eng.step(spawn_mode=2, tic=True, encode=True, auto_reset=True, random_actions=True, keys=True)
+        n = int(eng.row_count.item())
+        planes += n
+        csum += eng.keys[:n, 0].sum()
+    games = []
+    for gi in range(G):
+        g = orc.OracleGame(side, side, S, dec); g.init_native(seed, gi, 0); games.append(g)
+    st = orc.env_run(G, side, side, S, dec, 0.15, seed, tics, encode=True, n_threads=os.cpu_count() or 1, games=games)
+    tot = eng.totals()
+    assert tot["tics"] == st["steps"] == G * tics
+    assert tot["episodes"] == st["episodes"] and st["episodes"] > 0
+    assert [tot[k] for k in ("wall", "body", "head", "starve", "food_eaten", "game_length")] == st["counters"]
+    assert planes == st["planes"]
+    assert (int(csum.item()) & 0xFFFFFFFFFFFFFFFF) == st["plane_checksum"]
+    for gi in range(0, G, max(1, G // 257)):
+        want = games[gi].dump()
+        got = eng.get_state(gi)
+        assert_dump_equal(got, want, "game %d" % gi)
+        assert got["counters"][6] == want["counters"][6]   # episode
+    eng.close()
+
+
+def test_env_step_host_roundtrip():
+    """asz_env_step_host: host buffers in, host results out (the e2e path of bench.py)."""
+    import ctypes as C
+    import torch
+    from alphasnake_zero_b200 import _lib
+    eng = _engine(side=11, snakes=4, games=256, seed=3)
+    eng.reset()
+    G = 256
+    actions = torch.ones(G, 8, dtype=torch.uint8).pin_memory()
+    ended = torch.zeros(G, dtype=torch.uint8).pin_memory()
+    rewards = torch.zeros(G, 8, dtype=torch.int8).pin_memory()
+    planes = torch.zeros(G * 4, 21, 21, 3).pin_memory()
+    ids = torch.zeros(G * 4, dtype=torch.int32).pin_memory()
+    rows = C.c_int32(0)
+    L = _lib.lib()
+    flags = _lib.STEP_TIC | _lib.STEP_ENCODE
+    for t in range(5):
+        _lib.check(L.asz_env_step_host(eng.h, flags, 2, C.c_void_p(actions.data_ptr()), None,
+                                       C.c_void_p(ended.data_ptr()), C.c_void_p(rewards.data_ptr()), C.byref(rows),
+                                       C.c_void_p(planes.data_ptr()), C.c_void_p(ids.data_ptr()), eng.stream))
+    n = rows.value
+    assert 0 < n <= G * 4
+    # all snakes went straight for 5 tics from a start cell next to the wall: planes must match get_state-derived oracle
+    from oracle import oracle as orc
+    order = np.argsort(ids[:n].numpy())
+    for r in order[:64]:
+        gid, sid = int(ids[r]) // 8, int(ids[r]) % 8
+        g = orc.OracleGame(11, 11, 4, 1)
+        d = eng.get_state(gid)
+        g.load_dump(d)
+        k = g.live_ids().index(sid)
+        assert np.array_equal(g.make_state(k).view(np.uint32), planes[r].numpy().view(np.uint32))
+    eng.close()
+
+
+def test_no_cpu_fallback_symbols():
+    from alphasnake_zero_b200 import _lib
+    L = _lib.lib()
+    for name, _, _ in _lib.SYMBOLS:
+        assert hasattr(L, name)
