@@ -246,7 +246,7 @@ def run_ours(args, rank, world, local_rank):
                 "note": "asz_env_step_host: pinned host actions in, per-game ended/rewards + row count out; planes stay in HBM for the network"},
         "gpu_launches": K, "clocks": clocks,
     }
-    if world == 1:
+    if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
     if world > 1:
@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
