@@ -47,6 +47,22 @@ SYMBOLS = [
     ("asz_internal_planes", _vp, [_vp]),
     ("asz_internal_row_ids", _vp, [_vp]),
     ("asz_plane_floats", C.c_size_t, [_vp]),
+    ("asz_search_begin", C.c_int, [_vp, _vp]),
+    ("asz_search_epoch_begin", C.c_int, [_vp, _vp]),
+    ("asz_search_step_probe", C.c_int, [_vp, _vp, _vp]),
+    ("asz_search_step_sample", C.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    ("asz_search_finish", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    ("asz_search_stub_values", C.c_int, [_vp, _vp]),
+    ("asz_search_run_stub", C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    ("asz_obstacle_mask", C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    ("asz_search_clear", C.c_int, [_vp, _vp]),
+    ("asz_search_info", C.c_int, [_vp, _vp]),
+    ("asz_search_eval_planes", _vp, [_vp]),
+    ("asz_search_eval_values", _vp, [_vp]),
+    ("asz_search_root_q", _vp, [_vp]),
+    ("asz_search_root_moves", _vp, [_vp]),
+    ("asz_search_stats", C.c_int, [_vp, _vp]),
+    ("asz_search_table_dump", C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
 ]
 
 

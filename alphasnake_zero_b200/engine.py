@@ -128,3 +128,73 @@ class Engine:
         ids = self.row_ids[:n]
         order = torch.argsort(ids)
         return ids[order].cpu().numpy(), self.planes[:n][order]
+
+    # ---- search (Agent.make_moves) -------------------------------------------------------------------------------
+    def search_info(self):
+        info = np.zeros(8, np.int32)
+        check(self.L.asz_search_info(self.h, _np(info)))
+        return dict(zip(("P", "epochs", "max_steps", "n_sub", "max_rows", "table_log2", "root_turn", "epoch"), info.tolist()))
+
+    def _wrap(self, ptr, shape, dtype):
+        """torch view of an engine-owned device buffer (no copy)."""
+        n = int(np.prod(shape))
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        iface = {"shape": (n,), "typestr": {1: "|u1", 4: "<f4"}[itemsize] if dtype != torch.int32 else "<i4",
+                 "data": (int(ptr), False), "version": 3}
+        holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.device).view(dtype).view(*shape)
+
+    def search(self, value_fn=None, trace=None, trace_mode=0, root_trace=None):
+        """One root turn of the search for the engine's current root games.
+        value_fn(planes[n, N, N, 3] float32 cuda) -> [n, 3] float32 cuda raw network outputs (the obstacle mask of
+        AlphaNNet.v is applied here); None = the deterministic stub value function (no host sync in the loops).
+        trace: uint8 cuda tensor [epochs, max_steps, G*P, S]; trace_mode 0 none / 1 replay / 2 record.
+        Returns (root_q [G, 8, 3] float32, root_moves [G, 8] uint8, 255 = no row) as views of engine buffers."""
+        st = self.stream
+        tp = C.c_void_p(trace.data_ptr()) if trace is not None else None
+        rp = C.c_void_p(root_trace.data_ptr()) if root_trace is not None else None
+        if value_fn is None:
+            check(self.L.asz_search_run_stub(self.h, tp, trace_mode, rp, st))
+        else:
+            info = self.search_info()
+            planes = self._wrap(self.L.asz_search_eval_planes(self.h), (info["max_rows"], self.N, self.N, 3), torch.float32)
+            values = self._wrap(self.L.asz_search_eval_values(self.h), (info["max_rows"], 3), torch.float32)
+            n = C.c_int32(0)
+            check(self.L.asz_search_begin(self.h, st))
+            for _ in range(info["epochs"]):
+                check(self.L.asz_search_epoch_begin(self.h, st))
+                for step in range(1, info["max_steps"] + 2):
+                    check(self.L.asz_search_step_probe(self.h, C.byref(n), st))
+                    if step <= info["max_steps"]:
+                        if n.value > 0:
+                            v = value_fn(planes[:n.value])
+                            values[:n.value].copy_(v)
+                            check(self.L.asz_obstacle_mask(self.h, C.c_void_p(planes.data_ptr()), n.value,
+                                                           C.c_void_p(values.data_ptr()), st))
+                        check(self.L.asz_search_step_sample(self.h, None, tp, trace_mode, st))
+            check(self.L.asz_search_finish(self.h, rp, None, None, st))
+        q = self._wrap(self.L.asz_search_root_q(self.h), (self.G, 8, 3), torch.float32)
+        mv = self._wrap(self.L.asz_search_root_moves(self.h), (self.G, 8), torch.uint8)
+        return q, mv
+
+    def search_clear(self):
+        check(self.L.asz_search_clear(self.h, self.stream))
+
+    def search_stats(self):
+        s = np.zeros(16, np.uint64)
+        check(self.L.asz_search_stats(self.h, _np(s)))
+        names = ("evals", "node_visits", "hits", "subgames", "subgame_tics", "collisions", "inserts", "recreated",
+                 "occupied", "overflow")
+        return dict(zip(names, s.tolist()))
+
+    def table(self, cap=None):
+        cnt = C.c_int32(0)
+        check(self.L.asz_search_table_dump(self.h, 0, None, None, None, None, C.byref(cnt)))
+        n = cnt.value if cap is None else min(cap, cnt.value)
+        keys = np.zeros((max(n, 1), 2), np.uint64); W = np.zeros((max(n, 1), 3), np.float32); N = np.zeros((max(n, 1), 3), np.float32)
+        age = np.zeros(max(n, 1), np.int32)
+        if n > 0:
+            check(self.L.asz_search_table_dump(self.h, n, _np(keys), _np(W), _np(N), _np(age), C.byref(cnt)))
+        keys, W, N, age = keys[:n], W[:n], N[:n], age[:n]
+        order = np.lexsort((keys[:, 1], keys[:, 0]))
+        return dict(keys=keys[order], W=W[order], N=N[order], Q=(W / N)[order] if n else W, age=age[order])

@@ -128,6 +128,55 @@ float* asz_internal_planes(asz_engine* e);
 int32_t* asz_internal_row_ids(asz_engine* e);
 size_t asz_plane_floats(const asz_engine* e);
 
+/* ---- search: Agent.make_moves (agent.py:25-111) = epochs x (MCTSMPGameRunner.run, mp_game_runner.py:85-115, over
+ * MCTSAgent.make_moves, agent.py:161-223) ------------------------------------------------------------------------
+ * Call sequence for one root turn (what Agent.make_moves does for `games`, the engine's current root games):
+ *
+ *   asz_search_begin                                   ages the table (agent.py:30-31)
+ *   repeat max_breadth / min(8, max_breadth) times:    agent.py:37
+ *     asz_search_epoch_begin                           8 sub-games per live root game (agent.py:39-50)
+ *     for step = 1 .. max_depth + 1:
+ *       asz_search_step_probe  -> n_miss               tic of the previous step's moves, leave check and terminal
+ *                                                      backup (agent.py:60-72), keys, table probe, planes of the
+ *                                                      misses in asz_search_eval_planes() (agent.py:170-186)
+ *       <value network on n_miss planes, AlphaNNet.v contract, into asz_search_eval_values() or d_values>
+ *       asz_search_step_sample                         priors, softermax, sample, estimated reward (agent.py:193-214);
+ *                                                      skipped after the closing probe (step == max_depth + 1)
+ *   asz_search_finish                                  root Q and root moves (agent.py:74-99), eviction (agent.py:101-110)
+ *
+ * Trace buffers (device, uint8): tree moves [epochs][max_depth][games*P][S] indexed by absolute sub-game id
+ * game*P + sibling; trace_mode 0 = sample with the engine RNG, 1 = replay (read), 2 = sample and record (write).
+ * Root trace [games*8] by slot (replay of the root moves when training). */
+int asz_search_begin(asz_engine* e, void* stream);
+int asz_search_epoch_begin(asz_engine* e, void* stream);
+/* h_n_miss != NULL: synchronises the stream and returns the number of planes queued for the network */
+int asz_search_step_probe(asz_engine* e, int32_t* h_n_miss, void* stream);
+/* d_values: [n_miss][3] float32 network outputs WITH the obstacle mask applied, or NULL = asz_search_eval_values() */
+int asz_search_step_sample(asz_engine* e, const float* d_values, uint8_t* d_trace, int32_t trace_mode, void* stream);
+/* d_root_q [games*8*3], d_root_moves [games*8] (255 = no row) or NULL to keep them in the engine's buffers */
+int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_q, uint8_t* d_root_moves, void* stream);
+/* deterministic stub value function (value from the plane key + obstacle mask) on the queued planes; device side count */
+int asz_search_stub_values(asz_engine* e, void* stream);
+/* the whole sequence above with the stub value function and no host synchronisation in the loops */
+int asz_search_run_stub(asz_engine* e, uint8_t* d_trace, int32_t trace_mode, const uint8_t* d_root_trace, void* stream);
+/* AlphaNNet.v's obstacle mask (alpha_nnet.py:63-76) applied in place to d_values [n][3] for d_planes [n][plane] */
+int asz_obstacle_mask(asz_engine* e, const float* d_planes, int32_t n, float* d_values, void* stream);
+/* Agent.clear (agent.py:140-147): drops the table */
+int asz_search_clear(asz_engine* e, void* stream);
+/* h_info[8] = P (sub-games per root game), epochs, max steps, sub-games, max eval rows, table log2 capacity, root turn, epoch */
+int asz_search_info(asz_engine* e, int32_t* h_info);
+float* asz_search_eval_planes(asz_engine* e);   /* device [max eval rows][plane] float32 */
+float* asz_search_eval_values(asz_engine* e);   /* device [max eval rows][3] float32 */
+float* asz_search_root_q(asz_engine* e);        /* device [games*8][3] */
+uint8_t* asz_search_root_moves(asz_engine* e);  /* device [games*8] */
+/* h_stats[16] = evals, node visits, hits(unused), sub-games, sub-game tics, tag collisions, inserts, re-created,
+ * occupied slots, overflow, ... ; synchronous */
+int asz_search_stats(asz_engine* e, uint64_t* h_stats);
+/* live (not evicted) table entries: keys [cap*2], W [cap*3], N [cap*3], age [cap]; *h_count = live entries. Synchronous.
+ * Replaces inspection of Agent.cached_values / total_rewards / visit_cnts / cache_hit (agent.py:16-19); Q = W / N. */
+int asz_search_table_dump(asz_engine* e, int32_t cap, uint64_t* h_keys, float* h_w, float* h_n, int32_t* h_age,
+                          int32_t* h_count);
+
 #ifdef __cplusplus
 }
 #endif
