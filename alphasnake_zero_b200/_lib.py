@@ -44,6 +44,7 @@ SYMBOLS = [
     ("asz_env_step", C.c_int, [_vp, C.POINTER(StepArgs), _vp]),
     ("asz_env_step_host", C.c_int, [_vp, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("asz_get_totals", C.c_int, [_vp, _vp]),
+    ("asz_internal_state", C.c_int, [_vp, _vp]),
     ("asz_internal_planes", _vp, [_vp]),
     ("asz_internal_row_ids", _vp, [_vp]),
     ("asz_plane_floats", C.c_size_t, [_vp]),

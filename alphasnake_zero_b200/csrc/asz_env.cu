@@ -367,6 +367,11 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
   return ASZ_OK;
 }
 
+int asz_internal_state(asz_engine* e, void** d_ptrs) {
+  if (!e || !d_ptrs) { set_error("null argument"); return ASZ_ERR_ARG; }
+  d_ptrs[0] = e->root.cells; d_ptrs[1] = e->root.snakes; d_ptrs[2] = e->root.meta;
+  return ASZ_OK;
+}
 float* asz_internal_planes(asz_engine* e) { return e ? e->planes : nullptr; }
 int32_t* asz_internal_row_ids(asz_engine* e) { return e ? e->row_ids : nullptr; }
 size_t asz_plane_floats(const asz_engine* e) { return e ? (size_t)e->plane : 0; }

@@ -198,3 +198,35 @@ class Engine:
         keys, W, N, age = keys[:n], W[:n], N[:n], age[:n]
         order = np.lexsort((keys[:, 1], keys[:, 0]))
         return dict(keys=keys[order], W=W[order], N=N[order], Q=(W / N)[order] if n else W, age=age[order])
+
+    # ---- helpers for the drop-in classes ---------------------------------------------------------------------------
+    def alive_mask(self):
+        """bool [G, S] (device): snake alive and game not finished."""
+        if not hasattr(self, "_snk_view"):
+            ptrs = (C.c_void_p * 3)()
+            check(self.L.asz_internal_state(self.h, ptrs))
+            self._snk_view = self._wrap64(ptrs[1], (self.G, 8))
+            self._meta_view = self._wrap(ptrs[2], (self.G, 8), torch.int32)
+        alive = ((self._snk_view >> 42) & 1).bool()[:, :self.S]
+        live_game = (self._meta_view[:, 7] & 1) == 0
+        return alive & live_game[:, None]
+
+    def _wrap64(self, ptr, shape):
+        n = int(np.prod(shape))
+        iface = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+        holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.device).view(*shape)
+
+    def encode_rows(self, refresh=True):
+        """(planes [n, N, N, 3] device view, row ids numpy [n]) of the current root states."""
+        if refresh:
+            self.step(tic=False, encode=True)
+        n = int(self.row_count.item())
+        return self.planes[:n], self.row_ids[:n].cpu().numpy()
+
+    def states_of(self, game):
+        planes, rows = self.encode_rows()
+        sel = [i for i, r in enumerate(rows) if r // 8 == game]
+        sel.sort(key=lambda i: rows[i])
+        ph = planes.cpu().numpy()
+        return [ph[i] for i in sel]

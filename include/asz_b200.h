@@ -123,6 +123,11 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
  * then 7 reserved slots.  Synchronous. */
 int asz_get_totals(asz_engine* e, uint64_t* h_totals);
 
+/* device pointers of the packed root-game records, read-only for callers: d_ptrs[0] = cells (u16 [G][padded cells]),
+ * d_ptrs[1] = snakes (u64 [G][8]: head:16 | len:16 | health:8 | last_move:2 | alive:1 | reward:2), d_ptrs[2] = meta
+ * (u32 [G][8]: game_length, episode, wall, body, head, starve, food_eaten, flags bit0 = finished).  Replaces
+ * iterating `games` for liveness (mp_game_runner.py:40-42). */
+int asz_internal_state(asz_engine* e, void** d_ptrs);
 /* device pointer of the engine's internal plane buffer (capacity G*S rows) and row-id buffer */
 float* asz_internal_planes(asz_engine* e);
 int32_t* asz_internal_row_ids(asz_engine* e);

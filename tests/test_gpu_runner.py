@@ -1,0 +1,125 @@
+"""GPU: the drop-in classes (MPGameRunner / Agent / AlphaNNet / pit runner) keep the reference's surface and agree
+with the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests.helpers import assert_dump_equal
+
+pytestmark = pytest.mark.gpu
+
+
+class RandomAgent:
+    """any object with make_moves(games, ids) works as Alice (mp_game_runner.py:43)"""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+        self.log = []
+
+    def make_moves(self, games, ids):
+        mv = self.rng.integers(0, 3, size=len(ids)).tolist()
+        self.log.append((list(ids), mv))
+        return mv
+
+
+def test_runner_with_host_agent_matches_oracle():
+    from alphasnake_zero_b200.utils.mp_game_runner import MPGameRunner
+    from oracle import oracle as orc
+    G, seed = 48, 21
+    gr = MPGameRunner(11, 11, 4, 1, G, seed=seed, verbose=False)
+    alice = RandomAgent(3)
+    rewards = gr.run(alice)
+    assert len(rewards) == G and all(r is not None and len(r) == 4 for r in rewards)
+    games = []
+    for gi in range(G):
+        g = orc.OracleGame(11, 11, 4, 1); g.init_native(seed, gi, 0); games.append(g)
+    done = [False] * G
+    want = [None] * G
+    for ids, mv in alice.log:
+        per = {}
+        for (g, s), m in zip(ids, mv):
+            per.setdefault(g, []).append(m)
+        assert sorted(per.keys()) == [g for g in range(G) if not done[g]]
+        for g, ms in per.items():
+            assert [s for (gg, s) in ids if gg == g] == games[g].live_ids()     # ids order = live-list order
+            if games[g].tic(np.array(ms, np.int32), spawn_mode=2, chance=0.15, seed=seed):
+                done[g] = True
+                want[g] = [None if r == 0 else float(r) for r in games[g].dump()["snake"][:, 5]]
+    assert all(done)
+    assert rewards == want
+    tot = np.zeros(6)
+    for g in games:
+        tot += g.dump()["counters"][:6]
+    got = [gr.wall_collision, gr.body_collision, gr.head_collision, gr.starvation, gr.food_eaten, gr.game_length]
+    np.testing.assert_allclose(got, tot / G)
+    for r in rewards:
+        assert sum(1 for x in r if x == 1.0) <= 1 and all(x in (None, 1.0, -1.0) for x in r)
+
+
+def test_selfplay_with_search_agent_records():
+    from alphasnake_zero_b200.utils.agent import Agent, StubNet
+    from alphasnake_zero_b200.utils.mp_game_runner import MPGameRunner
+    G = 16
+    alice = Agent(StubNet(), 2, True, 8, 16)
+    gr = MPGameRunner(11, 11, 4, 1, G, seed=5, verbose=False, table_log2=18)
+    rewards = gr.run(alice)
+    assert len(alice.records) == len(alice.values) > G * 4
+    assert alice.records[0].shape == (21, 21, 3) and alice.values[0].shape == (3,)
+    assert all(r is not None for r in rewards)
+    assert gr.game_length > 1
+    # every record is a legal plane: own head at the centre, values within the reference's ranges
+    for p in alice.records[:50]:
+        assert np.all(p[10, 10] == -1.0)
+    alice.clear()
+    assert alice.records == [] and gr.engine.table()["keys"].shape[0] == 0
+
+
+def test_alphannet_torch_forward_matches_oracle():
+    import torch
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    from oracle import net_oracle as no
+    from oracle import oracle as orc
+    w = no.init_weights(11, seed=3, randomize_bn=True)
+    net = AlphaNNet(weights=w, backend="torch", dtype="fp32")
+    g = orc.OracleGame(); g.init_native(1, 0)
+    X = []
+    rng = np.random.default_rng(0)
+    for t in range(6):
+        X += g.get_states()
+        g.tic(rng.integers(0, 3, g.n_live).astype(np.int32), spawn_mode=2, seed=1)
+    X = np.array(X[:12], np.float32)
+    want = no.forward(w, X)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    got = net.forward_torch(torch.from_numpy(X).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-5)     # fp32 tolerance of BASELINE.json's north star
+    np.testing.assert_array_equal(net.v(X) == -1.0, no.v(w, X) == -1.0)
+    assert net.v(X).shape == (12, 3) and net.v(X).dtype == np.float32
+
+
+def test_pit_runner_and_pit_agent():
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    from alphasnake_zero_b200.utils.pit_agent import Agent as PitAgent
+    from alphasnake_zero_b200.utils.pit_mp_game_runner import MPGameRunner as PitRunner
+    a = AlphaNNet(input_shape=(21, 21, 3), seed=1, backend="torch", dtype="fp32")
+    b = AlphaNNet(input_shape=(21, 21, 3), seed=2, backend="torch", dtype="fp32")
+    gr = PitRunner(11, 11, 2, 1, 24, seed=4)
+    winners = gr.run(PitAgent(a), PitAgent(b), 1)
+    assert len(winners) == 24 and all(w in (None, 0, 1) for w in winners)
+    gr = PitRunner(11, 11, 4, 1, 8, seed=4)
+    winners = gr.run(PitAgent(a), PitAgent(b))
+    assert all(w in (None, 0, 1, 2, 3) for w in winners)
+
+
+def test_game_view_surface():
+    from alphasnake_zero_b200.utils.mp_game_runner import MPGameRunner
+    from oracle import oracle as orc
+    gr = MPGameRunner(11, 11, 4, 1, 3, seed=9, verbose=False)
+    gr._make_engine(RandomAgent(0))
+    g = gr.games[1]
+    og = orc.OracleGame(); og.init_native(9, 1, 0)
+    assert g.get_ids() == [(1, s) for s in range(4)]
+    st = g.get_states()
+    for k in range(4):
+        assert np.array_equal(st[k].view(np.uint32), og.make_state(k).view(np.uint32))
+    assert len(g.snakes) == 4 and g.snakes[0].length == 3 and g.rewards == [None] * 4
+    assert len(g.food) >= 2
