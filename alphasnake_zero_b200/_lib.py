@@ -29,6 +29,12 @@ class StepArgs(C.Structure):
                 ("d_rewards", C.c_void_p)]
 
 
+class NetWeights(C.Structure):
+    _fields_ = [("side", C.c_int32), ("w_conv", C.c_void_p * 9), ("scale", C.c_void_p * 9), ("bias", C.c_void_p * 9),
+                ("head_w", C.c_void_p), ("head_scale", C.c_float), ("head_bias", C.c_float), ("dense1_w", C.c_void_p),
+                ("dense1_b", C.c_void_p), ("dense2_w", C.c_void_p), ("dense2_b", C.c_void_p)]
+
+
 _lib = None
 
 # every symbol include/asz_b200.h declares: (name, restype, argtypes)
@@ -64,6 +70,9 @@ SYMBOLS = [
     ("asz_search_root_moves", _vp, [_vp]),
     ("asz_search_stats", C.c_int, [_vp, _vp]),
     ("asz_search_table_dump", C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    ("asz_net_create", C.c_int, [C.POINTER(_vp), C.POINTER(NetWeights), _i32]),
+    ("asz_net_destroy", C.c_int, [_vp]),
+    ("asz_net_forward", C.c_int, [_vp, _vp, _i32, _vp, _vp]),
 ]
 
 

@@ -1,0 +1,417 @@
+// asz_net.cu -- the value network of alpha_nnet.py:19-56 as hand-written sm_100a kernels (inference only).
+//
+// The only dense contraction of the self-play loop (99.7 % of the FLOPs are the eight 128->128 3x3 convolutions,
+// SURVEY.md 8(a) a14) runs as implicit GEMM on the 5th-generation tensor cores:
+//
+//   activations  bf16, "channel-chunk major": act[kc][pos][8] (kc = channel / 8), pos = flat position of a padded
+//                22x22 raster per image (21 real rows/cols + one zero row/col shared by neighbours), so that the
+//                input of tap (dy,dx) for output rows [m, m+128) is simply rows [m+s, m+s+128), s = (dy-1)*22+(dx-1);
+//   A operand    one halo tile (128 + 2*24 rows, all 16 channel chunks) per CTA, fetched once with cp.async.bulk and
+//                reused by all 9 taps through the shared-memory descriptor's start address (no-swizzle K-major core
+//                matrices: 8 rows x 16 B contiguous, SBO = 128 B => rows are linear, any row offset is legal);
+//   B operand    weights [tap][kc][cout][8] bf16 streamed tap by tap (32 KB) through a 3-stage mbarrier ring;
+//   D            128 x 128 fp32 accumulator in TMEM, 72 tcgen05.mma (M128 N128 K16) per tile issued by one thread;
+//   epilogue     4 warps read TMEM (tcgen05.ld 32x32b), apply the folded BatchNorm scale/bias, the residual add and
+//                the ReLU (alpha_nnet.py:22-47), zero the padding positions and store bf16 in the same layout; the
+//                last convolution instead applies the 1x1 head convolution + BN + ReLU (alpha_nnet.py:49-50).
+//   dense head   Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54): one CTA per image, fp32.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "asz_engine.hpp"
+
+namespace asz {
+
+constexpr int kC = 128;          // channels of the tower
+constexpr int kKC = kC / 8;      // 16-byte channel chunks
+constexpr int kTileM = 128;      // output rows (positions) per CTA
+constexpr int kHalo = 24;        // >= 23 = max |tap shift| for the 22-pitch raster
+constexpr int kGuard = 32;       // zero rows before and after the activation arrays
+constexpr int kStages = 3;
+
+__host__ __device__ constexpr int pitch_of(int side) { return 2 * side; }            // 2*side-1 real + 1 pad
+__host__ __device__ constexpr int img_rows_of(int side) { return 2 * side; }         // 2*side-1 real + 1 pad
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle: 8x(16 B) core matrices, LBO = byte distance between the two
+// 16-byte K chunks of one K=16 step, SBO = byte distance between 8-row groups (cute/arch/mma_sm100_desc.hpp layout:
+// start [0,14), LBO [16,30), SBO [32,46), version [46,48) = 1, layout type [61,64) = 0)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor kind::f16: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+// ---- convolution kernel -----------------------------------------------------------------------------------------
+struct ConvParams {
+  const __nv_bfloat16* in;     // [kc_in][P_tot][8]
+  const __nv_bfloat16* wt;     // [taps][kc_in][128][8]
+  const float* scale;          // [128] folded BN
+  const float* bias;           // [128]
+  const __nv_bfloat16* res;    // [16][P_tot][8] or null
+  __nv_bfloat16* out;          // [16][P_tot][8] or null (head mode)
+  const float* head_w;         // [128] or null
+  float head_scale, head_bias;
+  float* head_out;             // [P_tot] (head mode)
+  int kc_in;                   // 16, or 4 for the first layer's im2col input
+  int taps;                    // 9 or 1
+  int pitch;                   // raster pitch (22 at 11x11)
+  int img_stride;              // positions per image (pitch * rows)
+  int real;                    // real rows / cols per image (21)
+  int P_tot;                   // rows of every activation array (guards included)
+  int P_real;                  // positions that belong to images of this launch
+};
+
+constexpr int kRowsA = kTileM + 2 * kHalo;   // 176
+
+struct ConvSmem {
+  // A: [kc][176][16 B], B stages: [kc][128][16 B]
+  static constexpr size_t a_bytes = (size_t)kKC * kRowsA * 16;           // 45,056
+  static constexpr size_t b_bytes = (size_t)kKC * kC * 16;               // 32,768
+  static constexpr size_t total = a_bytes + kStages * b_bytes + 2 * kC * sizeof(float) * 2 + 256;
+};
+
+__global__ void __launch_bounds__(192, 1) conv_tile_kernel(const ConvParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + ConvSmem::a_bytes;
+  float* s_scale = reinterpret_cast<float*>(sB + kStages * ConvSmem::b_bytes);
+  float* s_bias = s_scale + kC;
+  float* s_head = s_bias + kC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_head + kC);   // [0] A full, [1..3] B full, [4..6] B empty, [7] acc full
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  const int m0 = (int)blockIdx.x * kTileM;                     // first output position of this tile (image space)
+  const int kc_in = p.kc_in, taps = p.taps;
+
+  for (int i = (int)threadIdx.x; i < kC; i += (int)blockDim.x) {
+    s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i];
+    s_head[i] = p.head_w ? p.head_w[i] : 0.0f;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars[1 + s], 1); mbar_init(&bars[4 + s], 1); }
+    mbar_init(&bars[7], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, kC);   // 128 fp32 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- producer: A halo tile once, then the weights tap by tap ----
+      const size_t row0 = (size_t)kGuard + (size_t)m0 - kHalo;   // first halo row in the global arrays
+      mbar_expect_tx(&bars[0], (uint32_t)(kc_in * kRowsA * 16));
+      for (int kc = 0; kc < kc_in; ++kc)
+        bulk_g2s(sA + (size_t)kc * kRowsA * 16, p.in + ((size_t)kc * p.P_tot + row0) * 8, kRowsA * 16, &bars[0]);
+      const uint32_t tap_bytes = (uint32_t)(kc_in * kC * 16);
+      for (int t = 0; t < taps; ++t) {
+        const int s = t % kStages;
+        if (t >= kStages) mbar_wait(&bars[4 + s], (uint32_t)(((t / kStages) - 1) & 1));
+        mbar_expect_tx(&bars[1 + s], tap_bytes);
+        bulk_g2s(sB + (size_t)s * ConvSmem::b_bytes, p.wt + (size_t)t * kc_in * kC * 8, tap_bytes, &bars[1 + s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      mbar_wait(&bars[0], 0);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      uint32_t acc = 0;
+      for (int t = 0; t < taps; ++t) {
+        const int s = t % kStages;
+        mbar_wait(&bars[1 + s], (uint32_t)((t / kStages) & 1));
+        tc_fence_after();
+        const int shift = (taps == 1) ? 0 : ((t / 3) - 1) * p.pitch + ((t % 3) - 1);
+        for (int ks = 0; ks < kc_in / 2; ++ks) {
+          const uint32_t a_addr = a_base + (uint32_t)(((2 * ks) * kRowsA + kHalo + shift) * 16);
+          const uint32_t b_addr = b_base + (uint32_t)(s * ConvSmem::b_bytes) + (uint32_t)((2 * ks) * kC * 16);
+          umma_bf16(tmem_d, smem_desc(a_addr, kRowsA * 16, 128), smem_desc(b_addr, kC * 16, 128), kIdesc, acc);
+          acc = 1;
+        }
+        umma_commit(&bars[4 + s]);   // frees this weight stage when the MMAs above have read it
+      }
+      umma_commit(&bars[7]);         // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // row of the tile == TMEM lane
+    const int pos = m0 + r;                      // image-space position
+    const int rem = pos % p.img_stride;
+    const int y = rem / p.pitch, x = rem - y * p.pitch;
+    const bool valid = pos < p.P_real && y < p.real && x < p.real;
+    const size_t grow = (size_t)kGuard + (size_t)pos;
+    mbar_wait(&bars[7], 0);
+    tc_fence_after();
+    float head_acc = 0.0f;
+#pragma unroll 1
+    for (int cb = 0; cb < kC / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        const int kc = cb * 4 + j8;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = kc * 8 + j;
+          f[j] = __uint_as_float(v[j8 * 8 + j]) * s_scale[c] + s_bias[c];
+        }
+        if (p.res != nullptr) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(p.res + ((size_t)kc * p.P_tot + grow) * 8);
+          const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 t2 = __bfloat1622float2(rb[j]); f[2 * j] += t2.x; f[2 * j + 1] += t2.y; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = valid ? fmaxf(f[j], 0.0f) : 0.0f;
+        if (p.out != nullptr) {
+          uint4 ov;
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          *reinterpret_cast<uint4*>(p.out + ((size_t)kc * p.P_tot + grow) * 8) = ov;
+        }
+        if (p.head_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // the head convolution reads the bf16-rounded activation, like every other consumer of this layer would
+            const float a = __bfloat162float(__float2bfloat16_rn(f[j]));
+            head_acc = fmaf(a, s_head[kc * 8 + j], head_acc);
+          }
+        }
+      }
+    }
+    if (p.head_out != nullptr)
+      p.head_out[grow] = valid ? fmaxf(head_acc * p.head_scale + p.head_bias, 0.0f) : 0.0f;   // alpha_nnet.py:49-50
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, kC); }
+}
+
+// ---- input preparation: fp32 NHWC planes -> bf16 im2col rows of the first convolution (K = 27 padded to 32) --------
+__global__ void im2col_kernel(const float* __restrict__ planes, int n_img, int real, int pitch, int img_stride, int P_tot,
+                              __nv_bfloat16* __restrict__ out /* [4][P_tot][8] */) {
+  const int pos = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (pos >= n_img * img_stride) return;
+  const int n = pos / img_stride, rem = pos - n * img_stride;
+  const int y = rem / pitch, x = rem - y * pitch;
+  float k[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) k[i] = 0.0f;
+  if (y < real && x < real) {
+    const float* pl = planes + (size_t)n * real * real * 3;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = y + dy - 1, xx = x + dx - 1;
+        if (yy >= 0 && yy < real && xx >= 0 && xx < real) {
+          const float* s = pl + ((size_t)yy * real + xx) * 3;
+          k[(dy * 3 + dx) * 3 + 0] = s[0]; k[(dy * 3 + dx) * 3 + 1] = s[1]; k[(dy * 3 + dx) * 3 + 2] = s[2];
+        }
+      }
+  }
+  const size_t grow = (size_t)kGuard + (size_t)pos;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint4 ov;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(k[kc * 8 + 2 * j], k[kc * 8 + 2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + ((size_t)kc * P_tot + grow) * 8) = ov;
+  }
+}
+
+// ---- dense head: Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54), one CTA per image ------------
+__global__ void __launch_bounds__(128) dense_head_kernel(const float* __restrict__ head /* [P_tot] */, int real, int pitch, int img_stride,
+                                                         const float* __restrict__ w1 /* [real*real][128] */, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2 /* [128][3] */, const float* __restrict__ b2,
+                                                         float* __restrict__ out /* [n][3] */) {
+  extern __shared__ float sh[];          // real*real + 128
+  float* s_in = sh;
+  float* s_h = sh + real * real;
+  const int n = (int)blockIdx.x, tid = (int)threadIdx.x;
+  const float* src = head + kGuard + (size_t)n * img_stride;
+  for (int i = tid; i < real * real; i += 128) { const int y = i / real, x = i - y * real; s_in[i] = src[y * pitch + x]; }
+  __syncthreads();
+  float acc = b1[tid];
+  for (int i = 0; i < real * real; ++i) acc = fmaf(s_in[i], w1[(size_t)i * 128 + tid], acc);
+  s_h[tid] = fmaxf(acc, 0.0f);
+  __syncthreads();
+  if (tid < 3) {
+    float o = b2[tid];
+    for (int j = 0; j < 128; ++j) o = fmaf(s_h[j], w2[j * 3 + tid], o);
+    out[(size_t)n * 3 + tid] = tanhf(o);
+  }
+}
+
+}  // namespace asz
+
+using namespace asz;
+
+struct asz_net {
+  asz_net_weights w;
+  int side = 0, real = 0, pitch = 0, img_stride = 0;
+  int chunk = 0;           // images per pass
+  int P_tot = 0;           // rows of the activation arrays (guards + padded positions)
+  __nv_bfloat16* act[3] = {nullptr, nullptr, nullptr};
+  __nv_bfloat16* col = nullptr;   // im2col input of the first layer [4][P_tot][8]
+  float* head = nullptr;          // [P_tot]
+};
+
+extern "C" {
+
+int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images) {
+  if (!out || !w) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if (w->side != 7 && w->side != 11 && w->side != 19) { set_error("side must be 7, 11 or 19"); return ASZ_ERR_ARG; }
+  if (chunk_images < 1) { set_error("chunk_images must be >= 1"); return ASZ_ERR_ARG; }
+  asz_net* n = new asz_net();
+  n->w = *w;
+  n->side = w->side; n->real = 2 * w->side - 1; n->pitch = pitch_of(w->side); n->img_stride = n->pitch * img_rows_of(w->side);
+  if (n->pitch + 1 > kHalo) { set_error("board too large for the halo of conv_tile_kernel"); delete n; return ASZ_ERR_ARG; }
+  n->chunk = chunk_images;
+  const size_t P = (size_t)chunk_images * n->img_stride;
+  const size_t P_pad = (P + kTileM - 1) / kTileM * kTileM;
+  n->P_tot = (int)(kGuard + P_pad + kGuard + kHalo);
+  const size_t act_bytes = (size_t)kKC * n->P_tot * 8 * sizeof(__nv_bfloat16);
+  for (int i = 0; i < 3; ++i) {
+    ASZ_CUDA(cudaMalloc(&n->act[i], act_bytes));
+    ASZ_CUDA(cudaMemset(n->act[i], 0, act_bytes));
+  }
+  ASZ_CUDA(cudaMalloc(&n->col, (size_t)4 * n->P_tot * 8 * sizeof(__nv_bfloat16)));
+  ASZ_CUDA(cudaMemset(n->col, 0, (size_t)4 * n->P_tot * 8 * sizeof(__nv_bfloat16)));
+  ASZ_CUDA(cudaMalloc(&n->head, (size_t)n->P_tot * sizeof(float)));
+  ASZ_CUDA(cudaMemset(n->head, 0, (size_t)n->P_tot * sizeof(float)));
+  ASZ_CUDA(cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvSmem::total));
+  *out = n;
+  return ASZ_OK;
+}
+
+int asz_net_destroy(asz_net* n) {
+  if (!n) return ASZ_OK;
+  for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
+  cudaFree(n->col); cudaFree(n->head);
+  delete n;
+  return ASZ_OK;
+}
+
+static int launch_conv(asz_net* n, int layer, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* outp, bool head,
+                       int n_img, cudaStream_t st) {
+  ConvParams p;
+  memset(&p, 0, sizeof p);
+  p.in = in; p.wt = reinterpret_cast<const __nv_bfloat16*>(n->w.w_conv[layer]);
+  p.scale = n->w.scale[layer]; p.bias = n->w.bias[layer];
+  p.res = res; p.out = outp;
+  if (head) { p.head_w = n->w.head_w; p.head_scale = n->w.head_scale; p.head_bias = n->w.head_bias; p.head_out = n->head; }
+  p.kc_in = layer == 0 ? 4 : kKC; p.taps = layer == 0 ? 1 : 9;
+  p.pitch = n->pitch; p.img_stride = n->img_stride; p.real = n->real; p.P_tot = n->P_tot;
+  p.P_real = n_img * n->img_stride;
+  const int tiles = (p.P_real + kTileM - 1) / kTileM;
+  conv_tile_kernel<<<tiles, 192, ConvSmem::total, st>>>(p);
+  return cuda_ok(cudaGetLastError(), "conv_tile_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
+}
+
+int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_values, void* stream) {
+  if (!n || !d_planes || !d_values) { set_error("null argument"); return ASZ_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t plane = (size_t)n->real * n->real * 3;
+  for (int i0 = 0; i0 < count; i0 += n->chunk) {
+    const int m = std::min(n->chunk, count - i0);
+    const int P = m * n->img_stride;
+    im2col_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_planes + (size_t)i0 * plane, m, n->real, n->pitch, n->img_stride, n->P_tot, n->col);
+    if (!cuda_ok(cudaGetLastError(), "im2col_kernel")) return ASZ_ERR_CUDA;
+    int rc = launch_conv(n, 0, n->col, nullptr, n->act[0], false, m, st);          // alpha_nnet.py:21-22
+    if (rc != ASZ_OK) return rc;
+    int x = 0;                                                                     // index of the block input
+    for (int b = 0; b < 4; ++b) {                                                  // alpha_nnet.py:24-47
+      const int t = (x + 1) % 3, y = (x + 2) % 3;
+      rc = launch_conv(n, 1 + 2 * b, n->act[x], nullptr, n->act[t], false, m, st);
+      if (rc != ASZ_OK) return rc;
+      const bool last = b == 3;
+      rc = launch_conv(n, 2 + 2 * b, n->act[t], n->act[x], last ? nullptr : n->act[y], last, m, st);
+      if (rc != ASZ_OK) return rc;
+      x = y;
+    }
+    dense_head_kernel<<<m, 128, (size_t)(n->real * n->real + 128) * sizeof(float), st>>>(
+        n->head, n->real, n->pitch, n->img_stride, n->w.dense1_w, n->w.dense1_b, n->w.dense2_w, n->w.dense2_b, d_values + (size_t)i0 * 3);
+    if (!cuda_ok(cudaGetLastError(), "dense_head_kernel")) return ASZ_ERR_CUDA;
+  }
+  return ASZ_OK;
+}
+
+}  // extern "C"

@@ -182,6 +182,36 @@ int asz_search_stats(asz_engine* e, uint64_t* h_stats);
 int asz_search_table_dump(asz_engine* e, int32_t cap, uint64_t* h_keys, float* h_w, float* h_n, int32_t* h_age,
                           int32_t* h_count);
 
+/* ---- value network: AlphaNNet.v_net.predict (alpha_nnet.py:19-56, 62), inference only --------------------------
+ * Weights are passed as DEVICE pointers in the layouts the kernels consume (alphasnake_zero_b200/net.py builds them
+ * from the Keras-layout arrays: conv kernels HWIO, dense (in, out), BN gamma/beta/moving mean/variance, eps 1e-3):
+ *   w_conv[0]     bf16 [1][4][128][8]   first convolution as a K=32 GEMM over im2col rows, k = (dy*3+dx)*3 + c
+ *   w_conv[1..8]  bf16 [9][16][128][8]  [tap = dy*3+dx][cin / 8][cout][cin % 8]
+ *   scale/bias    fp32 [128]            BatchNorm folded: y = conv * scale + bias
+ *   head_w        fp32 [128]            1x1 head convolution; head_scale/head_bias = its folded BatchNorm
+ *   dense1_w      fp32 [(2*side-1)^2][128], dense1_b [128], dense2_w [128][3], dense2_b [3] */
+typedef struct {
+  int32_t side;
+  const void* w_conv[9];
+  const float* scale[9];
+  const float* bias[9];
+  const float* head_w;
+  float head_scale;
+  float head_bias;
+  const float* dense1_w;
+  const float* dense1_b;
+  const float* dense2_w;
+  const float* dense2_b;
+} asz_net_weights;
+
+typedef struct asz_net asz_net;
+/* chunk_images: images processed per pass (sizes the activation workspace: ~31 KB... 124 KB per image and buffer) */
+int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images);
+int asz_net_destroy(asz_net* net);
+/* d_planes [count][2*side-1][2*side-1][3] float32 NHWC -> d_values [count][3] float32 tanh outputs (no obstacle mask;
+ * asz_obstacle_mask applies AlphaNNet.v's mask).  bf16 operands, fp32 accumulation. */
+int asz_net_forward(asz_net* net, const float* d_planes, int32_t count, float* d_values, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,60 @@
+"""GPU numerics of the value network: the hand-written tcgen05 kernels against the float64 CPU restatement
+(oracle/net_oracle.py; TF itself is not runnable here, see its header) and against the plain PyTorch forward.
+Tolerance: 2e-2 absolute on the tanh outputs for the bf16 path, 1e-5 for the fp32 PyTorch path (BASELINE.json)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def game_planes(side, S, n, seed=1):
+    from oracle import oracle as orc
+    rng = np.random.default_rng(seed)
+    X = []
+    gid = 0
+    while len(X) < n:
+        g = orc.OracleGame(side, side, S, 1); g.init_native(seed, gid); gid += 1
+        for t in range(30):
+            X += g.get_states()
+            if g.tic(rng.integers(0, 3, g.n_live).astype(np.int32), spawn_mode=2, seed=seed):
+                break
+    return np.array(X[:n], np.float32)
+
+
+@pytest.mark.parametrize("side,S,n,chunk", [(11, 4, 37, 1024), (11, 4, 300, 128), (7, 4, 20, 64), (19, 8, 9, 16)])
+def test_native_net_matches_oracle(side, S, n, chunk):
+    import torch
+    from alphasnake_zero_b200.net import NativeNet
+    from oracle import net_oracle as no
+    w = no.init_weights(side, seed=5, randomize_bn=True)
+    # scale the kernels up so that the outputs use a good part of the tanh range
+    for k in list(w.keys()):
+        if k.startswith("dense2_w"):
+            w[k] = (w[k] * 6).astype(np.float32)
+    X = game_planes(side, S, n)
+    want = no.forward(w, X[:min(n, 48)])
+    net = NativeNet(w, "cuda", chunk_images=chunk)
+    got = net.forward(torch.from_numpy(X).cuda()).cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got[:len(want)] - want).max()
+    assert err < 2e-2, err
+    assert np.abs(want).max() > 0.05          # the comparison is not vacuous
+    # batch invariance: the same plane gives the same bits wherever it sits in the batch
+    perm = np.random.default_rng(0).permutation(n)
+    got2 = net.forward(torch.from_numpy(X[perm]).cuda()).cpu().numpy()
+    assert np.array_equal(got2.view(np.uint32), got[perm].view(np.uint32))
+
+
+def test_native_net_vs_torch_bf16_and_alphannet_v():
+    import torch
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    from oracle import net_oracle as no
+    w = no.init_weights(11, seed=9, randomize_bn=True)
+    X = game_planes(11, 4, 64, seed=3)
+    a = AlphaNNet(weights=w, backend="native")
+    b = AlphaNNet(weights=w, backend="torch", dtype="fp32")
+    va, vb = a.v(X), b.v(X)
+    assert va.shape == vb.shape == (64, 3) and va.dtype == np.float32
+    assert np.array_equal(va == -1.0, vb == -1.0)          # obstacle mask identical
+    assert np.abs(va - vb).max() < 2e-2
+    assert a._get_native() is not None
