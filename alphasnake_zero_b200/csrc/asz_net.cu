@@ -28,8 +28,8 @@ namespace asz {
 constexpr int kC = 128;          // channels of the tower
 constexpr int kKC = kC / 8;      // 16-byte channel chunks
 constexpr int kTileM = 128;      // output rows (positions) per CTA
-constexpr int kHalo = 24;        // >= 23 = max |tap shift| for the 22-pitch raster
-constexpr int kGuard = 32;       // zero rows before and after the activation arrays
+constexpr int kHalo = 40;        // >= pitch + 1 = max |tap shift| (39 for the 38-pitch raster of 19x19 boards)
+constexpr int kGuard = 48;       // zero rows before and after the activation arrays
 constexpr int kStages = 3;
 
 __host__ __device__ constexpr int pitch_of(int side) { return 2 * side; }            // 2*side-1 real + 1 pad
@@ -130,11 +130,11 @@ struct ConvParams {
   int P_real;                  // positions that belong to images of this launch
 };
 
-constexpr int kRowsA = kTileM + 2 * kHalo;   // 176
+constexpr int kRowsA = kTileM + 2 * kHalo;   // 208
 
 struct ConvSmem {
-  // A: [kc][176][16 B], B stages: [kc][128][16 B]
-  static constexpr size_t a_bytes = (size_t)kKC * kRowsA * 16;           // 45,056
+  // A: [kc][208][16 B], B stages: [kc][128][16 B]
+  static constexpr size_t a_bytes = (size_t)kKC * kRowsA * 16;           // 53,248
   static constexpr size_t b_bytes = (size_t)kKC * kC * 16;               // 32,768
   static constexpr size_t total = a_bytes + kStages * b_bytes + 2 * kC * sizeof(float) * 2 + 256;
 };
@@ -334,6 +334,8 @@ struct asz_net {
   float* head = nullptr;          // [P_tot]
 };
 
+static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st);
+
 extern "C" {
 
 int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images) {
@@ -388,8 +390,42 @@ static int launch_conv(asz_net* n, int layer, const __nv_bfloat16* in, const __n
 
 int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_values, void* stream) {
   if (!n || !d_planes || !d_values) { set_error("null argument"); return ASZ_ERR_ARG; }
-  cudaStream_t st = (cudaStream_t)stream;
+  return net_forward_impl(n, d_planes, count, d_values, -1, nullptr, (cudaStream_t)stream);
+}
+
+int asz_net_debug_layer(asz_net* n, const float* d_planes, int32_t count, int32_t layer, float* d_act, void* stream) {
+  if (!n || !d_planes || !d_act) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if (count > n->chunk) { set_error("debug export handles one chunk"); return ASZ_ERR_ARG; }
+  if (layer < 0 || layer > 8) { set_error("layer must be in 0..8"); return ASZ_ERR_ARG; }
+  return net_forward_impl(n, d_planes, count, nullptr, layer, d_act, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace asz {
+// activation buffer -> fp32 [n][real][real][128] (debug / tests)
+__global__ void export_act_kernel(const __nv_bfloat16* act, const float* head, int n_img, int real, int pitch, int img_stride, int P_tot,
+                                  float* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)real * real * (head ? 1 : kC);
+  if (i >= (size_t)n_img * per) return;
+  const int n = (int)(i / per);
+  size_t r = i - (size_t)n * per;
+  int c = 0;
+  if (!head) { c = (int)(r % kC); r /= kC; }
+  const int y = (int)(r / real), x = (int)(r % real);
+  const size_t grow = (size_t)kGuard + (size_t)n * img_stride + (size_t)y * pitch + x;
+  out[i] = head ? head[grow] : __bfloat162float(act[((size_t)(c >> 3) * P_tot + grow) * 8 + (c & 7)]);
+}
+}  // namespace asz
+
+static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st) {
   const size_t plane = (size_t)n->real * n->real * 3;
+  auto dump = [&](const __nv_bfloat16* act, const float* head, int m) -> int {
+    const size_t tot = (size_t)m * n->real * n->real * (head ? 1 : kC);
+    export_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(act, head, m, n->real, n->pitch, n->img_stride, n->P_tot, d_act);
+    return cuda_ok(cudaGetLastError(), "export_act_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
+  };
   for (int i0 = 0; i0 < count; i0 += n->chunk) {
     const int m = std::min(n->chunk, count - i0);
     const int P = m * n->img_stride;
@@ -397,14 +433,17 @@ int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_v
     if (!cuda_ok(cudaGetLastError(), "im2col_kernel")) return ASZ_ERR_CUDA;
     int rc = launch_conv(n, 0, n->col, nullptr, n->act[0], false, m, st);          // alpha_nnet.py:21-22
     if (rc != ASZ_OK) return rc;
+    if (stop_layer == 0) return dump(n->act[0], nullptr, m);
     int x = 0;                                                                     // index of the block input
     for (int b = 0; b < 4; ++b) {                                                  // alpha_nnet.py:24-47
       const int t = (x + 1) % 3, y = (x + 2) % 3;
       rc = launch_conv(n, 1 + 2 * b, n->act[x], nullptr, n->act[t], false, m, st);
       if (rc != ASZ_OK) return rc;
+      if (stop_layer == 1 + 2 * b) return dump(n->act[t], nullptr, m);
       const bool last = b == 3;
       rc = launch_conv(n, 2 + 2 * b, n->act[t], n->act[x], last ? nullptr : n->act[y], last, m, st);
       if (rc != ASZ_OK) return rc;
+      if (stop_layer == 2 + 2 * b) return last ? dump(nullptr, n->head, m) : dump(n->act[y], nullptr, m);
       x = y;
     }
     dense_head_kernel<<<m, 128, (size_t)(n->real * n->real + 128) * sizeof(float), st>>>(
@@ -413,5 +452,3 @@ int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_v
   }
   return ASZ_OK;
 }
-
-}  // extern "C"

@@ -91,3 +91,12 @@ class NativeNet:
             st = C.c_void_p(torch.cuda.current_stream(planes.device).cuda_stream)
             check(self.L.asz_net_forward(self.h, C.c_void_p(planes.data_ptr()), n, C.c_void_p(out.data_ptr()), st))
         return out
+
+    def debug_layer(self, planes, layer):
+        """test hook: output of convolution `layer` as float32 [n, N, N, 128] (layer 8: [n, N, N, 1], the head conv)."""
+        planes = planes.contiguous()
+        n = planes.shape[0]
+        out = torch.empty(n, self.N, self.N, 1 if layer == 8 else 128, dtype=torch.float32, device=planes.device)
+        st = C.c_void_p(torch.cuda.current_stream(planes.device).cuda_stream)
+        check(self.L.asz_net_debug_layer(self.h, C.c_void_p(planes.data_ptr()), n, layer, C.c_void_p(out.data_ptr()), st))
+        return out

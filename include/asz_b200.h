@@ -211,6 +211,9 @@ int asz_net_destroy(asz_net* net);
 /* d_planes [count][2*side-1][2*side-1][3] float32 NHWC -> d_values [count][3] float32 tanh outputs (no obstacle mask;
  * asz_obstacle_mask applies AlphaNNet.v's mask).  bf16 operands, fp32 accumulation. */
 int asz_net_forward(asz_net* net, const float* d_planes, int32_t count, float* d_values, void* stream);
+/* test hook: runs the tower up to convolution `layer` (0 = first conv, 1..8 = residual convs in order) and exports
+ * that layer's output as float32 [count][2*side-1][2*side-1][128] ([..][1] for layer 8: the fused 1x1 head conv) */
+int asz_net_debug_layer(asz_net* net, const float* d_planes, int32_t count, int32_t layer, float* d_act, void* stream);
 
 #ifdef __cplusplus
 }

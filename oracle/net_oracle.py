@@ -64,15 +64,45 @@ def _bn(x, p):
     return g * (x - m) / np.sqrt(v + BN_EPS) + b
 
 
-def forward(w, X, dtype=np.float64):
-    """X [B, n, n, 3] -> [B, 3] raw tanh outputs (no obstacle mask)."""
-    x = np.asarray(X, dtype=dtype)
+def bf16_round(a):
+    """round-to-nearest-even to bfloat16, returned as float64 (what the bf16 tensor-core path stores)."""
+    f = np.ascontiguousarray(a, dtype=np.float32)
+    u = f.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).astype(np.float64).reshape(f.shape)
+
+
+def forward_layers(w, X, bf16=True):
+    """outputs of the 9 tower convolutions (after BN / residual / ReLU; the last one after the 1x1 head conv too)."""
+    x = np.asarray(X, dtype=np.float64)
+    q = bf16_round if bf16 else (lambda a: a)
     relu = lambda a: np.maximum(a, 0)
-    h = relu(_bn(_conv_same(x, w["conv0"]), w["bn0"]))
+    outs = []
+    h = q(relu(_bn(_conv_same(q(x), q(w["conv0"])), w["bn0"])))
+    outs.append(h)
     for b in range(4):
         sc = h
-        h = relu(_bn(_conv_same(h, w["res%d_conv0" % b]), w["res%d_bn0" % b]))
-        h = relu(_bn(_conv_same(h, w["res%d_conv1" % b]), w["res%d_bn1" % b]) + sc)
+        h = q(relu(_bn(_conv_same(h, q(w["res%d_conv0" % b])), w["res%d_bn0" % b])))
+        outs.append(h)
+        h = q(relu(_bn(_conv_same(h, q(w["res%d_conv1" % b])), w["res%d_bn1" % b]) + sc))
+        outs.append(h)
+    outs[-1] = relu(_bn(_conv_same(h, w["head_conv"]), w["head_bn"]))
+    return outs
+
+
+def forward(w, X, dtype=np.float64, bf16=False):
+    """X [B, n, n, 3] -> [B, 3] raw tanh outputs (no obstacle mask).
+    bf16=True emulates the storage precision of the CUDA path: bf16 input planes, conv kernels and layer outputs
+    (exact products, wide accumulation), fp32/64 everywhere else."""
+    x = np.asarray(X, dtype=dtype)
+    q = bf16_round if bf16 else (lambda a: a)
+    relu = lambda a: np.maximum(a, 0)
+    x = q(x)
+    h = q(relu(_bn(_conv_same(x, q(w["conv0"])), w["bn0"])))
+    for b in range(4):
+        sc = h
+        h = q(relu(_bn(_conv_same(h, q(w["res%d_conv0" % b])), w["res%d_bn0" % b])))
+        h = q(relu(_bn(_conv_same(h, q(w["res%d_conv1" % b])), w["res%d_bn1" % b]) + sc))
     h = relu(_bn(_conv_same(h, w["head_conv"]), w["head_bn"]))
     h = h.reshape(h.shape[0], -1)
     h = relu(h.dot(w["dense1_w"].astype(dtype)) + w["dense1_b"].astype(dtype))
