@@ -101,6 +101,56 @@ def cpu_baseline(target_s=12.0):
                       % (g, tics, st["planes"] / st["steps"], cores, dt)}
 
 
+def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True):
+    """configs[2] of BASELINE.json (scaled by --sp-games): self-play root turns with the search kernels and the
+    hand-written value network.  A simulation = one sub-game rollout (agent.py:37-56)."""
+    import torch
+    from alphasnake_zero_b200.engine import Engine
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    from alphasnake_zero_b200 import _lib
+    eng = Engine(side=SIDE, snakes=SNAKES, health_dec=HEALTH_DEC, food_chance=CHANCE, games=games, seed=77 + rank,
+                 max_depth=depth, max_breadth=breadth, softmax_base=2.0, training=True)
+    eng.reset()
+    net = AlphaNNet(input_shape=(2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0, backend="native") if use_net else None
+    vf = net.v_device if use_net else None
+
+    def root_turn():
+        q, mv = eng.search(value_fn=vf)
+        act = torch.where(mv < 3, mv, torch.ones_like(mv))
+        eng.step(actions=act, spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=False, auto_reset=True)
+    for _ in range(warm):
+        root_turn()
+    torch.cuda.synchronize()
+    s0 = eng.search_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(turns):
+        root_turn()
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    s1 = eng.search_stats()
+    d = {k: s1[k] - s0[k] for k in ("evals", "node_visits", "subgames", "subgame_tics")}
+    out = {"workload": "configs[2]: %d games x breadth %d (%d sims/move), depth %d, base 2, %s, Q cache on" %
+                       (games, breadth, (breadth // min(8, breadth)) * min(8, breadth), depth,
+                        "bf16 tcgen05 value net (random init)" if use_net else "stub value function (search kernels only)"),
+           "root_turns": turns, "seconds": dt, "sims_per_sec": d["subgames"] / dt, "node_visits_per_sec": d["node_visits"] / dt,
+           "nn_evals_per_sec": d["evals"] / dt, "subgame_tics_per_sec": d["subgame_tics"] / dt,
+           "hit_rate": 1.0 - d["evals"] / max(d["node_visits"], 1), "evals_per_sim": d["evals"] / max(d["subgames"], 1),
+           "table_overflow": s1["overflow"], "tag_collisions": s1["collisions"]}
+    if use_net:
+        flops = 1043724288
+        out["net_tflops"] = d["evals"] * flops / dt / 1e12
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+            out["net_roofline"] = {"bound": "tensor", "achieved": out["net_tflops"], "peak": pk, "unit": "TFLOP/s",
+                                   "frac": out["net_tflops"] / pk}
+        except Exception:
+            pass
+    eng.close()
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -246,6 +296,12 @@ def run_ours(args, rank, world, local_rank):
                 "note": "asz_env_step_host: pinned host actions in, per-game ended/rewards + row count out; planes stay in HBM for the network"},
         "gpu_launches": K, "clocks": clocks,
     }
+    if not args.no_selfplay:
+        try:
+            out["mcts"] = selfplay_leg(rank, args.sp_games, 100, 8, args.sp_turns, 1, use_net=True)
+            out["mcts_search_only"] = selfplay_leg(rank, args.sp_games, 100, 8, args.sp_turns, 1, use_net=False)
+        except Exception as ex:   # the headline line must still be printed
+            out["mcts"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
@@ -260,6 +316,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play (MCTS + value net) leg")
+    ap.add_argument("--sp-games", type=int, default=1024, help="root games of the self-play leg (configs[2] uses 4096)")
+    ap.add_argument("--sp-turns", type=int, default=2, help="timed root turns of the self-play leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
