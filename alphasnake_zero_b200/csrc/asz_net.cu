@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -263,6 +264,180 @@ __global__ void __launch_bounds__(192, 1) conv_tile_kernel(const ConvParams p) {
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, kC); }
 }
 
+// ---- persistent convolution kernel (v2) -----------------------------------------------------------------------------
+// One CTA per SM loops over super-tiles of 256 positions.  Per super-tile the weights stream through shared memory
+// once (half a tap = 16 KB per stage) and feed two M=128 accumulators, so the L2 -> SM weight traffic per output row is
+// half of conv_tile_kernel's; TMEM holds two accumulator pairs (4 x 128 columns) so that the epilogue of super-tile i
+// overlaps the MMAs of super-tile i+1, and the activation halo tile is double buffered the same way.
+//   warp 0      producer  : cp.async.bulk of the A halo tile and of the weight chunks, mbarrier complete_tx
+//   warp 1      MMA issuer: one thread, tcgen05.mma M128 N128 K16, tcgen05.commit releases stages / publishes accumulators
+//   warps 2..5  epilogue  : tcgen05.ld, BN scale/bias, residual, ReLU, padding mask, bf16 store (or the fused head conv)
+template <int HALO>
+struct PersistSmem {
+  static constexpr int kSuper = 256;
+  static constexpr int rows = kSuper + 2 * HALO;
+  static constexpr size_t a_bytes = (size_t)kKC * rows * 16;
+  static constexpr size_t b_chunk = (size_t)8 * kC * 16;     // half a tap
+  static constexpr int b_stages = 3;
+  static constexpr size_t total = 2 * a_bytes + b_stages * b_chunk + 3 * kC * sizeof(float) + 16 * sizeof(uint64_t) + 64;
+};
+
+template <int HALO>
+__global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p, int n_super) {
+  using SM = PersistSmem<HALO>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + 2 * SM::a_bytes;
+  float* s_scale = reinterpret_cast<float*>(sB + SM::b_stages * SM::b_chunk);
+  float* s_bias = s_scale + kC;
+  float* s_head = s_bias + kC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_head + kC);
+  uint64_t* a_full = bars;          // [2]
+  uint64_t* a_empty = bars + 2;     // [2]
+  uint64_t* b_full = bars + 4;      // [3]
+  uint64_t* b_empty = bars + 7;     // [3]
+  uint64_t* acc_full = bars + 10;   // [2]
+  uint64_t* acc_empty = bars + 12;  // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  const int kc_in = p.kc_in, taps = p.taps;
+  const int kc_chunk = kc_in < 8 ? kc_in : 8;
+  const int chunks_per_tap = kc_in / kc_chunk;
+  const uint32_t chunk_bytes = (uint32_t)(kc_chunk * kC * 16);
+
+  for (int i = (int)threadIdx.x; i < kC; i += (int)blockDim.x) {
+    s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i];
+    s_head[i] = p.head_w ? p.head_w[i] : 0.0f;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < SM::b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t bit = 0;   // weight-chunk counter
+      uint32_t it = 0;    // super-tile counter of this CTA
+      for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
+        const int buf = (int)(it & 1u);
+        mbar_wait(&a_empty[buf], ((it >> 1) & 1u) ^ 1u);
+        const size_t row0 = (size_t)kGuard + (size_t)st * SM::kSuper - HALO;
+        mbar_expect_tx(&a_full[buf], (uint32_t)(kc_in * SM::rows * 16));
+        for (int kc = 0; kc < kc_in; ++kc)
+          bulk_g2s(sA + buf * SM::a_bytes + (size_t)kc * SM::rows * 16, p.in + ((size_t)kc * p.P_tot + row0) * 8, SM::rows * 16, &a_full[buf]);
+        for (int t = 0; t < taps; ++t)
+          for (int c = 0; c < chunks_per_tap; ++c, ++bit) {
+            const int s = (int)(bit % SM::b_stages);
+            mbar_wait(&b_empty[s], ((bit / SM::b_stages) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[s], chunk_bytes);
+            bulk_g2s(sB + (size_t)s * SM::b_chunk, p.wt + ((size_t)t * kc_in + (size_t)c * kc_chunk) * kC * 8, chunk_bytes, &b_full[s]);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t bit = 0, it = 0;
+      const uint32_t a_base0 = smem_u32(sA), b_base = smem_u32(sB);
+      for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
+        const int buf = (int)(it & 1u);
+        const uint32_t ph = (it >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], ph ^ 1u);     // the epilogue has drained this accumulator pair
+        mbar_wait(&a_full[buf], ph);
+        tc_fence_after();
+        const uint32_t a_base = a_base0 + (uint32_t)(buf * SM::a_bytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+        uint32_t first = 1;
+        for (int t = 0; t < taps; ++t) {
+          const int shift = (taps == 1) ? 0 : ((t / 3) - 1) * p.pitch + ((t % 3) - 1);
+          for (int c = 0; c < chunks_per_tap; ++c, ++bit) {
+            const int s = (int)(bit % SM::b_stages);
+            mbar_wait(&b_full[s], (bit / SM::b_stages) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              for (int ks = 0; ks < kc_chunk / 2; ++ks) {
+                const int kc = c * kc_chunk + 2 * ks;
+                const uint32_t a_addr = a_base + (uint32_t)((kc * SM::rows + HALO + shift + sub * kTileM) * 16);
+                const uint32_t b_addr = b_base + (uint32_t)(s * SM::b_chunk) + (uint32_t)((2 * ks) * kC * 16);
+                umma_bf16(tmem_d + (uint32_t)(sub * kC), smem_desc(a_addr, SM::rows * 16, 128), smem_desc(b_addr, kC * 16, 128), kIdesc,
+                          (first && ks == 0) ? 0u : 1u);
+              }
+            }
+            first = 0;
+            umma_commit(&b_empty[s]);
+          }
+        }
+        umma_commit(&acc_full[buf]);
+        umma_commit(&a_empty[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
+      const int buf = (int)(it & 1u);
+      mbar_wait(&acc_full[buf], (it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const int pos = st * SM::kSuper + sub * kTileM + q * 32 + lane;
+        const int rem = pos % p.img_stride;
+        const int y = rem / p.pitch, x = rem - y * p.pitch;
+        const bool valid = pos < p.P_real && y < p.real && x < p.real;
+        const size_t grow = (size_t)kGuard + (size_t)pos;
+        float head_acc = 0.0f;
+#pragma unroll 1
+        for (int cb = 0; cb < kC / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t)(buf * 256 + sub * kC + cb * 32) + ((uint32_t)(q * 32) << 16), v);
+          uint4 rv[4];
+          if (p.res != nullptr) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) rv[j8] = *reinterpret_cast<const uint4*>(p.res + ((size_t)(cb * 4 + j8) * p.P_tot + grow) * 8);
+          }
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int kc = cb * 4 + j8;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * s_scale[kc * 8 + j] + s_bias[kc * 8 + j];
+            if (p.res != nullptr) {
+              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[j8]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 t2 = __bfloat1622float2(rb[j]); f[2 * j] += t2.x; f[2 * j + 1] += t2.y; }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = valid ? fmaxf(f[j], 0.0f) : 0.0f;
+            if (p.out != nullptr) {
+              uint4 ov;
+              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              *reinterpret_cast<uint4*>(p.out + ((size_t)kc * p.P_tot + grow) * 8) = ov;
+            }
+            if (p.head_out != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) head_acc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), s_head[kc * 8 + j], head_acc);
+            }
+          }
+        }
+        if (p.head_out != nullptr) p.head_out[grow] = valid ? fmaxf(head_acc * p.head_scale + p.head_bias, 0.0f) : 0.0f;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ---- input preparation: fp32 NHWC planes -> bf16 im2col rows of the first convolution (K = 27 padded to 32) --------
 __global__ void im2col_kernel(const float* __restrict__ planes, int n_img, int real, int pitch, int img_stride, int P_tot,
                               __nv_bfloat16* __restrict__ out /* [4][P_tot][8] */) {
@@ -332,6 +507,8 @@ struct asz_net {
   __nv_bfloat16* act[3] = {nullptr, nullptr, nullptr};
   __nv_bfloat16* col = nullptr;   // im2col input of the first layer [4][P_tot][8]
   float* head = nullptr;          // [P_tot]
+  int n_sm = 148;
+  int variant = 2;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_persist_kernel)
 };
 
 static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st);
@@ -348,7 +525,7 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
   if (n->pitch + 1 > kHalo) { set_error("board too large for the halo of conv_tile_kernel"); delete n; return ASZ_ERR_ARG; }
   n->chunk = chunk_images;
   const size_t P = (size_t)chunk_images * n->img_stride;
-  const size_t P_pad = (P + kTileM - 1) / kTileM * kTileM;
+  const size_t P_pad = (P + 255) / 256 * 256;
   n->P_tot = (int)(kGuard + P_pad + kGuard + kHalo);
   const size_t act_bytes = (size_t)kKC * n->P_tot * 8 * sizeof(__nv_bfloat16);
   for (int i = 0; i < 3; ++i) {
@@ -360,6 +537,16 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
   ASZ_CUDA(cudaMalloc(&n->head, (size_t)n->P_tot * sizeof(float)));
   ASZ_CUDA(cudaMemset(n->head, 0, (size_t)n->P_tot * sizeof(float)));
   ASZ_CUDA(cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvSmem::total));
+  ASZ_CUDA(cudaFuncSetAttribute(conv_persist_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistSmem<24>::total));
+  ASZ_CUDA(cudaFuncSetAttribute(conv_persist_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistSmem<40>::total));
+  {
+    int dev = 0; cudaDeviceProp prop;
+    ASZ_CUDA(cudaGetDevice(&dev));
+    ASZ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    n->n_sm = prop.multiProcessorCount;
+    const char* v = getenv("ASZ_NET_VARIANT");
+    if (v && v[0] == '1') n->variant = 1;
+  }
   *out = n;
   return ASZ_OK;
 }
@@ -383,9 +570,16 @@ static int launch_conv(asz_net* n, int layer, const __nv_bfloat16* in, const __n
   p.kc_in = layer == 0 ? 4 : kKC; p.taps = layer == 0 ? 1 : 9;
   p.pitch = n->pitch; p.img_stride = n->img_stride; p.real = n->real; p.P_tot = n->P_tot;
   p.P_real = n_img * n->img_stride;
-  const int tiles = (p.P_real + kTileM - 1) / kTileM;
-  conv_tile_kernel<<<tiles, 192, ConvSmem::total, st>>>(p);
-  return cuda_ok(cudaGetLastError(), "conv_tile_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
+  if (n->variant == 1) {
+    const int tiles = (p.P_real + kTileM - 1) / kTileM;
+    conv_tile_kernel<<<tiles, 192, ConvSmem::total, st>>>(p);
+    return cuda_ok(cudaGetLastError(), "conv_tile_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
+  }
+  const int n_super = (p.P_real + 255) / 256;
+  const int grid = std::min(n_super, n->n_sm);
+  if (n->pitch + 1 <= 24) conv_persist_kernel<24><<<grid, 192, PersistSmem<24>::total, st>>>(p, n_super);
+  else conv_persist_kernel<40><<<grid, 192, PersistSmem<40>::total, st>>>(p, n_super);
+  return cuda_ok(cudaGetLastError(), "conv_persist_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
 }
 
 int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_values, void* stream) {
