@@ -64,17 +64,25 @@ __device__ __forceinline__ void store_meta(uint32_t* gm, const Meta& m, int lane
 }
 
 // ---- the fused step kernel ----------------------------------------------------------------------------------------
-template <int SIDE, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) env_step_kernel(const EnvParams p) {
+template <int SIDE, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvParams p) {
   using G = Geo<SIDE>;
+  using E = EncGeo<G>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_cnt[WARPS];
   __shared__ int s_base;
   __shared__ unsigned long long s_tot[8];
   const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
-  float* stage = reinterpret_cast<float*>(smem_raw) + warp * G::STAGE;
-  uint16_t* sb = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * G::STAGE * sizeof(float)) + warp * G::PC;
+  // smem: [per-CTA wall pattern][per warp: 2 staging buffers][per warp: board]
+  float* s_bg = reinterpret_cast<float*>(smem_raw);
+  float* stage0 = s_bg + E::BGLEN + warp * 2 * E::WSTAGE;
+  uint16_t* sb = reinterpret_cast<uint16_t*>(s_bg + E::BGLEN + WARPS * 2 * E::WSTAGE) + warp * G::PC;
   if (threadIdx.x < 8) s_tot[threadIdx.x] = 0ull;
+  if (p.flags & ASZ_STEP_ENCODE) {
+    fill_wall_pattern(s_bg, E::BGLEN, (int)threadIdx.x, WARPS * 32);
+    fill_wall_pattern(stage0, E::WSTAGE, lane, 32);
+    fill_wall_pattern(stage0 + E::WSTAGE, E::WSTAGE, lane, 32);
+  }
   __syncthreads();
 
   const int g = (int)blockIdx.x * WARPS + warp;
@@ -150,6 +158,10 @@ __global__ void __launch_bounds__(WARPS * 32) env_step_kernel(const EnvParams p)
   int row = s_base + s_cnt[warp];
   CellView<G> cv;
   warp_cell_view<G>(sb, sn, cv);
+  EncodeCtx<G> ctx;
+  ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg;
+#pragma unroll
+  for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
   unsigned rest = live_mask;
   while (rest) {
     const int vs = __ffs(rest) - 1;
@@ -157,15 +169,16 @@ __global__ void __launch_bounds__(WARPS * 32) env_step_kernel(const EnvParams p)
     if (row < p.max_rows) {
       uint64_t k0 = 0, k1 = 0;
       if (p.flags & ASZ_STEP_KEYS) {
-        warp_encode<G, true>(cv, sn, vs, stage, p.planes, (size_t)row * G::PLANE, &k0, &k1);
+        warp_encode_v2<G, true>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, &k0, &k1);
         if (lane == 0) { p.keys[2 * (size_t)row] = k0; p.keys[2 * (size_t)row + 1] = k1; }
       } else {
-        warp_encode<G, false>(cv, sn, vs, stage, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
+        warp_encode_v2<G, false>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
       }
       if (lane == 0) p.row_ids[row] = g * 8 + vs;
     }
     ++row;
   }
+  if (lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the copy engine has read it
 }
 
 // ---- reset kernel ---------------------------------------------------------------------------------------------------
@@ -189,18 +202,25 @@ __global__ void __launch_bounds__(WARPS * 32) env_reset_kernel(uint16_t* cells, 
 template <int SIDE>
 struct EnvLaunch {
   static constexpr int WARPS = (SIDE >= 19) ? 4 : 8;
+  static constexpr int MINB = (SIDE >= 19) ? 2 : 4;
   using G = Geo<SIDE>;
-  static size_t smem_bytes() { return (size_t)WARPS * (G::STAGE * sizeof(float) + G::PC * sizeof(uint16_t)); }
+  using E = EncGeo<G>;
+  static size_t smem_bytes() {
+    return (size_t)(E::BGLEN + WARPS * 2 * E::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t);
+  }
   static int step(const EnvParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_bytes()), "cudaFuncSetAttribute(env_step_kernel)"))
+        return ASZ_ERR_CUDA;
+      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
         return ASZ_ERR_CUDA;
       configured = true;
     }
     const int blocks = (p.G + WARPS - 1) / WARPS;
-    env_step_kernel<SIDE, WARPS><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
+    env_step_kernel<SIDE, WARPS, MINB><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
     return cuda_ok(cudaGetLastError(), "env_step_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
   }
   static int reset(const GameSet& gs, int S, uint64_t seed, cudaStream_t st) {

@@ -325,4 +325,144 @@ __device__ __forceinline__ void warp_encode(const CellView<G>& cv, const Snake& 
   }
 }
 
+
+// ---- plane encode, v2: window staging + bulk async stores --------------------------------------------------------
+// A plane is 21x21x3 floats of which only the 11 rows that intersect the board window are not pure wall background.
+// Those rows (one contiguous element range [W0, W1) of the plane) are staged in a per-warp buffer whose background is
+// written once per kernel (stage[s] = 1 iff s % 3 == 1); per plane the warp scatters its board cells into it, hands the
+// plane to the bulk-copy engine as three cp.async.bulk shared->global stores (wall before the window from a per-CTA
+// constant buffer, the window, wall after) and later restores the touched pixels.  The staging offset `off` makes the
+// shared and global addresses agree modulo 16 bytes (planes are only 4-byte aligned: 1323 floats) and modulo the 3-float
+// pixel pattern.  Compared with v1 the warp no longer fills and copies the whole plane with LSU instructions.
+template <class G>
+struct EncGeo {
+  static constexpr int WIN = G::SIDE * 3 * G::N;                       // floats of the window rows (693 at 11x11)
+  static constexpr int WSTAGE = ((12 + WIN + 4 + 3) / 4) * 4;          // staging floats per buffer
+  static constexpr int BGLEN = ((8 + (G::N - G::SIDE) * 3 * G::N + 4 + 3) / 4) * 4;   // per-CTA wall pattern
+};
+
+template <class G>
+struct EncodeCtx {
+  float* cur;            // staging buffer of the next plane
+  float* oth;            // the other buffer (its bulk store may still be in flight)
+  const float* bg;
+  int prev_cur[G::CPL];  // stage index of the pixel each of this lane's cells was scattered to in `cur` (-1 none)
+  int prev_oth[G::CPL];
+};
+
+__device__ __forceinline__ void fill_wall_pattern(float* dst, int n_floats, int tid, int nthreads) {
+  for (int q4 = tid; q4 < n_floats / 4; q4 += nthreads) {
+    const int r = q4 % 3;   // element 4*q4 has phase (4*q4) % 3 == q4 % 3
+    float4 v;
+    v.x = (r == 1) ? 1.0f : 0.0f; v.y = (r == 0) ? 1.0f : 0.0f; v.z = (r == 2) ? 1.0f : 0.0f; v.w = v.x;
+    reinterpret_cast<float4*>(dst)[q4] = v;
+  }
+}
+__device__ __forceinline__ void bulk_s2g(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class G, bool kWantKey>
+__device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snake& sn, int vs, EncodeCtx<G>& ctx, float* out,
+                                               size_t gidx0, uint64_t* key0, uint64_t* key1) {
+  constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS, N = G::N, PLANE = G::PLANE;
+  using E = EncGeo<G>;
+  const int lane = lane_id();
+  const int vhead = __shfl_sync(kFull, sn.head, vs);
+  const int vlen = __shfl_sync(kFull, sn.len, vs);
+  const int vhp = __shfl_sync(kFull, sn.health, vs);
+  const int vrot = __shfl_sync(kFull, sn.last, vs);
+  const int hy = vhead / SIDE, hx = vhead - hy * SIDE;
+  const float my_hv = (float)(((double)sn.len - ((double)vlen - 0.5)) * 0.04);
+  const float foodv = (float)((double)(101 - vhp) * 0.01);
+  // first output row of the window after rot90 (game.py:249-257)
+  const int i0 = (vrot == 0) ? SIDE - 1 - hy : (vrot == 1) ? hx : (vrot == 2) ? hy : SIDE - 1 - hx;
+  const int W0 = i0 * 3 * N, W1 = W0 + E::WIN;
+  const int a = (int)((gidx0 + (size_t)W0) & 3);
+  const int off = (9 * a) % 12;             // off % 4 == a, off % 3 == 0
+  float* stage = ctx.cur;
+  // the bulk store that read this buffer two planes ago must have finished reading it
+  if (lane == 0) bulk_wait_read<1>();
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int s = ctx.prev_cur[q];
+    if (s >= 0) { stage[s] = 0.0f; stage[s + 1] = 1.0f; stage[s + 2] = 0.0f; }
+  }
+  __syncwarp();
+  uint64_t k0 = 0, k1 = 0;
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane * CPL + q;
+    const int hsq = cv.hs[q];
+    const float hv = __shfl_sync(kFull, my_hv, hsq < 0 ? 0 : hsq);
+    int sidx = -1;
+    if (c < CELLS) {
+      const int y = c / SIDE, x = c - y * SIDE;
+      const int gy = y - hy + (SIDE - 1), gx = x - hx + (SIDE - 1);
+      int i, j;
+      if (vrot == 0) { i = gy; j = gx; }
+      else if (vrot == 1) { i = N - 1 - gx; j = gy; }
+      else if (vrot == 2) { i = N - 1 - gy; j = N - 1 - gx; }
+      else { i = gx; j = N - 1 - gy; }
+      const int p = i * N + j;
+      float t0, t1, t2;
+      if (c == vhead) { t0 = t1 = t2 = -1.0f; }
+      else { t0 = (hsq >= 0) ? hv : 0.0f; t1 = cv.f1[q]; t2 = cv.food[q] ? foodv : 0.0f; }
+      if (out != nullptr) {
+        sidx = 3 * p - W0 + off;
+        stage[sidx] = t0; stage[sidx + 1] = t1; stage[sidx + 2] = t2;
+      }
+      if (kWantKey) key_accumulate((uint32_t)p, __float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), k0, k1);
+    }
+    ctx.prev_cur[q] = sidx;
+  }
+  if (kWantKey) {
+    k0 = warp_sum_u64(k0); k1 = warp_sum_u64(k1);
+    if (k0 == 0) k0 = 1;
+    *key0 = k0; *key1 = k1;
+  }
+  if (out == nullptr) return;
+  fence_proxy_async_smem();
+  __syncwarp();
+  const size_t gA = (gidx0 + 3) & ~(size_t)3, gend = gidx0 + PLANE, gE = gend & ~(size_t)3;
+  const size_t gw0 = gidx0 + (size_t)W0, gw1 = gidx0 + (size_t)W1;
+  size_t GA = gw0 & ~(size_t)3, GE = (gw1 + 3) & ~(size_t)3;       // aligned cover of the window
+  if (GA < gA) GA = gA;
+  if (GE > gE) GE = gE;
+  if (lane == 0) {
+    if (GA > gA) {                                                   // wall before the window
+      const int e_s = (int)(gA - gidx0);
+      bulk_s2g(out + gA, ctx.bg + 4 * (e_s % 3), (uint32_t)((GA - gA) * 4));
+    }
+    // window: plane element e sits at stage[e - W0 + off]
+    bulk_s2g(out + GA, stage + ((long long)(GA - gidx0) - W0 + off), (uint32_t)((GE - GA) * 4));
+    if (gE > GE) {                                                   // wall after the window
+      const int e_s = (int)(GE - gidx0);
+      bulk_s2g(out + GE, ctx.bg + 4 * (e_s % 3), (uint32_t)((gE - GE) * 4));
+    }
+    bulk_commit();
+  } else if (lane <= 6) {
+    // up to 3 floats before the first and after the last 16-byte boundary of the plane
+    const int k = lane - 1;                                          // 0..2 head, 3..5 tail
+    const int nhead = (int)(gA - gidx0), ntail = (int)(gend - gE);
+    int e = -1;
+    if (k < 3) { if (k < nhead) e = k; }
+    else if (k - 3 < ntail) e = (int)(gE - gidx0) + (k - 3);
+    if (e >= 0) {
+      const float v = (e >= W0 && e < W1) ? stage[e - W0 + off] : ((e % 3 == 1) ? 1.0f : 0.0f);
+      out[gidx0 + e] = v;
+    }
+  }
+  ctx.cur = ctx.oth; ctx.oth = stage;
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) { const int t = ctx.prev_cur[q]; ctx.prev_cur[q] = ctx.prev_oth[q]; ctx.prev_oth[q] = t; }
+}
+
 }  // namespace asz
