@@ -5,7 +5,9 @@
 // every surviving snake (5,292 B each at 11x11) straight into the network's input batch with 16-byte stores.
 // Rows of the batch are handed out by one atomicAdd per CTA after a block-level scan of the live counts.
 // Roofline: HBM write bandwidth (planes are > 95 % of the bytes).
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -64,13 +66,13 @@ __device__ __forceinline__ void store_meta(uint32_t* gm, const Meta& m, int lane
 }
 
 // ---- the fused step kernel ----------------------------------------------------------------------------------------
+// Persistent: MINB CTAs per SM, every warp loops over games g = warp_global, warp_global + n_warps, ... so that the
+// staging buffers' wall background is written once per warp and bulk stores of one game overlap the tic of the next.
 template <int SIDE, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvParams p) {
   using G = Geo<SIDE>;
   using E = EncGeo<G>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_cnt[WARPS];
-  __shared__ int s_base;
   __shared__ unsigned long long s_tot[8];
   const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
   // smem: [per-CTA wall pattern][per warp: 2 staging buffers][per warp: board]
@@ -78,21 +80,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   float* stage0 = s_bg + E::BGLEN + warp * 2 * E::WSTAGE;
   uint16_t* sb = reinterpret_cast<uint16_t*>(s_bg + E::BGLEN + WARPS * 2 * E::WSTAGE) + warp * G::PC;
   if (threadIdx.x < 8) s_tot[threadIdx.x] = 0ull;
-  if (p.flags & ASZ_STEP_ENCODE) {
+  const bool enc = (p.flags & ASZ_STEP_ENCODE) != 0;
+  if (enc) {
     fill_wall_pattern(s_bg, E::BGLEN, (int)threadIdx.x, WARPS * 32);
     fill_wall_pattern(stage0, E::WSTAGE, lane, 32);
     fill_wall_pattern(stage0 + E::WSTAGE, E::WSTAGE, lane, 32);
   }
   __syncthreads();
+  EncodeCtx<G> ctx;
+  ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg;
+#pragma unroll
+  for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
+  unsigned long long t_tics = 0, t_planes = 0;   // lane 0 accumulates, flushed once per warp
 
-  const int g = (int)blockIdx.x * WARPS + warp;
-  const bool valid = g < p.G;
-  Snake sn; sn.head = 0xFFFF; sn.len = 0; sn.health = 0; sn.last = 0; sn.alive = 0; sn.reward = 0;
-  Meta m; m.turn = m.episode = m.wall = m.body = m.headc = m.starve = m.eaten = 0; m.flags = 1;
-  if (valid) {
+  const int n_warps = (int)gridDim.x * WARPS;
+  for (int g = (int)blockIdx.x * WARPS + warp; g < p.G; g += n_warps) {
     load_board<G>(p.cells + (size_t)g * G::PC, sb, lane);
+    Snake sn; sn.head = 0xFFFF; sn.len = 0; sn.health = 0; sn.last = 0; sn.alive = 0; sn.reward = 0;
     if (lane < 8) sn = unpack_snake(p.snakes[(size_t)g * 8 + lane]);
-    m = load_meta(p.meta + (size_t)g * 8, lane);
+    Meta m = load_meta(p.meta + (size_t)g * 8, lane);
     __syncwarp();
     if ((p.flags & ASZ_STEP_TIC) && !(m.flags & 1u)) {
       int move = 1;
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         p.rewards[(size_t)g * 8 + lane] = (int8_t)(sn.reward == 1 ? 1 : sn.reward == 2 ? -1 : 0);
       if (lane == 0) {
         if (p.ended != nullptr) p.ended[g] = r.ended ? 1 : 0;
-        atomicAdd(&s_tot[7], 1ull);
+        t_tics += 1;
         if (r.ended) {   // mp_game_runner.py:56-61
           atomicAdd(&s_tot[0], (unsigned long long)m.wall); atomicAdd(&s_tot[1], (unsigned long long)m.body);
           atomicAdd(&s_tot[2], (unsigned long long)m.headc); atomicAdd(&s_tot[3], (unsigned long long)m.starve);
@@ -121,64 +127,58 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       }
       if (r.ended && (p.flags & ASZ_STEP_AUTO_RESET)) warp_init_native<G>(sb, sn, m, p.S, p.seed, (uint32_t)g, m.episode + 1);
       // write the record back
-      {
-        uint16_t* gc = p.cells + (size_t)g * G::PC;
-        if constexpr (G::CPL % 4 == 0) {
+      uint16_t* gc = p.cells + (size_t)g * G::PC;
+      if constexpr (G::CPL % 4 == 0) {
 #pragma unroll
-          for (int q = 0; q < G::CPL / 4; ++q)
-            reinterpret_cast<uint2*>(gc)[lane * (G::CPL / 4) + q] = reinterpret_cast<const uint2*>(sb)[lane * (G::CPL / 4) + q];
-        } else {
+        for (int q = 0; q < G::CPL / 4; ++q)
+          reinterpret_cast<uint2*>(gc)[lane * (G::CPL / 4) + q] = reinterpret_cast<const uint2*>(sb)[lane * (G::CPL / 4) + q];
+      } else {
 #pragma unroll
-          for (int q = 0; q < G::CPL / 2; ++q)
-            reinterpret_cast<uint32_t*>(gc)[lane * (G::CPL / 2) + q] = reinterpret_cast<const uint32_t*>(sb)[lane * (G::CPL / 2) + q];
-        }
-        if (lane < 8) p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
-        store_meta(p.meta + (size_t)g * 8, m, lane);
+        for (int q = 0; q < G::CPL / 2; ++q)
+          reinterpret_cast<uint32_t*>(gc)[lane * (G::CPL / 2) + q] = reinterpret_cast<const uint32_t*>(sb)[lane * (G::CPL / 2) + q];
       }
+      if (lane < 8) p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
+      store_meta(p.meta + (size_t)g * 8, m, lane);
     } else if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) {
       p.ended[g] = 0;
     }
-  }
-  // ---- row allocation: block scan of live counts, one atomic per CTA ----
-  const unsigned live_mask = __ballot_sync(kFull, sn.alive != 0);
-  const bool do_encode = (p.flags & ASZ_STEP_ENCODE) && valid && !(m.flags & 1u);
-  const int n_rows = do_encode ? __popc(live_mask) : 0;
-  if (lane == 0) s_cnt[warp] = n_rows;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
-    s_base = tot > 0 ? atomicAdd(p.row_count, tot) : 0;
-    if (tot > 0) atomicAdd(&p.totals[8], (unsigned long long)tot);
-  }
-  if (threadIdx.x < 8 && s_tot[threadIdx.x] != 0ull) atomicAdd(&p.totals[threadIdx.x], s_tot[threadIdx.x]);
-  __syncthreads();
-  if (n_rows == 0) return;
-  int row = s_base + s_cnt[warp];
-  CellView<G> cv;
-  warp_cell_view<G>(sb, sn, cv);
-  EncodeCtx<G> ctx;
-  ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg;
-#pragma unroll
-  for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
-  unsigned rest = live_mask;
-  while (rest) {
-    const int vs = __ffs(rest) - 1;
-    rest &= rest - 1;
-    if (row < p.max_rows) {
-      uint64_t k0 = 0, k1 = 0;
-      if (p.flags & ASZ_STEP_KEYS) {
-        warp_encode_v2<G, true>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, &k0, &k1);
-        if (lane == 0) { p.keys[2 * (size_t)row] = k0; p.keys[2 * (size_t)row + 1] = k1; }
-      } else {
-        warp_encode_v2<G, false>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
+    // ---- rows of this game: one atomicAdd per warp (rows of a game stay contiguous, ascending snake id) ----
+    if (enc && !(m.flags & 1u)) {
+      const unsigned live_mask = __ballot_sync(kFull, sn.alive != 0);
+      const int n_rows = __popc(live_mask);
+      if (n_rows > 0) {
+        int row = 0;
+        if (lane == 0) { row = atomicAdd(p.row_count, n_rows); t_planes += (unsigned long long)n_rows; }
+        row = __shfl_sync(kFull, row, 0);
+        CellView<G> cv;
+        warp_cell_view<G>(sb, sn, cv);
+        unsigned rest = live_mask;
+        while (rest) {
+          const int vs = __ffs(rest) - 1;
+          rest &= rest - 1;
+          if (row < p.max_rows) {
+            uint64_t k0 = 0, k1 = 0;
+            if (p.flags & ASZ_STEP_KEYS) {
+              warp_encode_v2<G, true>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, &k0, &k1);
+              if (lane == 0) { p.keys[2 * (size_t)row] = k0; p.keys[2 * (size_t)row + 1] = k1; }
+            } else {
+              warp_encode_v2<G, false>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
+            }
+            if (lane == 0) p.row_ids[row] = g * 8 + vs;
+          }
+          ++row;
+        }
       }
-      if (lane == 0) p.row_ids[row] = g * 8 + vs;
     }
-    ++row;
+    __syncwarp();   // the board buffer is reused by the next game
   }
-  if (lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the copy engine has read it
+  if (lane == 0) {
+    bulk_wait_read<0>();   // shared memory must stay valid until the copy engine has read it
+    if (t_tics) atomicAdd(&s_tot[7], t_tics);
+    if (t_planes) atomicAdd(&p.totals[8], t_planes);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_tot[threadIdx.x] != 0ull) atomicAdd(&p.totals[threadIdx.x], s_tot[threadIdx.x]);
 }
 
 // ---- reset kernel ---------------------------------------------------------------------------------------------------
@@ -202,14 +202,15 @@ __global__ void __launch_bounds__(WARPS * 32) env_reset_kernel(uint16_t* cells, 
 template <int SIDE>
 struct EnvLaunch {
   static constexpr int WARPS = (SIDE >= 19) ? 4 : 8;
-  static constexpr int MINB = (SIDE >= 19) ? 2 : 4;
   using G = Geo<SIDE>;
   using E = EncGeo<G>;
   static size_t smem_bytes() {
     return (size_t)(E::BGLEN + WARPS * 2 * E::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t);
   }
-  static int step(const EnvParams& p, cudaStream_t st) {
+  template <int MINB>
+  static int launch(const EnvParams& p, cudaStream_t st) {
     static bool configured = false;
+    static int n_sm = 0;
     if (!configured) {
       if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_bytes()), "cudaFuncSetAttribute(env_step_kernel)"))
@@ -217,11 +218,21 @@ struct EnvLaunch {
       if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
         return ASZ_ERR_CUDA;
+      int dev = 0;
+      if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return ASZ_ERR_CUDA;
+      if (!cuda_ok(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return ASZ_ERR_CUDA;
       configured = true;
     }
-    const int blocks = (p.G + WARPS - 1) / WARPS;
+    const int blocks = std::min((p.G + WARPS - 1) / WARPS, n_sm * MINB);
     env_step_kernel<SIDE, WARPS, MINB><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
     return cuda_ok(cudaGetLastError(), "env_step_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
+  }
+  static int step(const EnvParams& p, cudaStream_t st) {
+    static int minb = -1;
+    if (minb < 0) { const char* v = getenv("ASZ_ENV_MINB"); minb = v ? atoi(v) : 0; }
+    if (SIDE >= 19) return launch<2>(p, st);
+    if (minb == 4) return launch<4>(p, st);
+    return launch<3>(p, st);
   }
   static int reset(const GameSet& gs, int S, uint64_t seed, cudaStream_t st) {
     const int blocks = (gs.n + WARPS - 1) / WARPS;

@@ -235,6 +235,7 @@ struct CellView {
   float f1[G::CPL];
   int8_t hs[G::CPL];
   bool food[G::CPL];
+  int8_t cy[G::CPL], cx[G::CPL];   // (y, x) of this lane's cells: constants of the thread
 };
 template <class G>
 __device__ __forceinline__ void warp_cell_view(const uint16_t* sb, const Snake& sn, CellView<G>& cv) {
@@ -249,6 +250,8 @@ __device__ __forceinline__ void warp_cell_view(const uint16_t* sb, const Snake& 
     cv.f1[q] = body ? (float)((double)d * 0.02) : 0.0f;
     cv.hs[q] = (int8_t)((body && d == len_o) ? o : -1);
     cv.food[q] = (v == kFood);
+    const int c = lane * G::CPL + q;
+    cv.cy[q] = (int8_t)(c / G::SIDE); cv.cx[q] = (int8_t)(c - (c / G::SIDE) * G::SIDE);
   }
 }
 
@@ -381,11 +384,18 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   const int hy = vhead / SIDE, hx = vhead - hy * SIDE;
   const float my_hv = (float)(((double)sn.len - ((double)vlen - 0.5)) * 0.04);
   const float foodv = (float)((double)(101 - vhp) * 0.01);
-  // first output row of the window after rot90 (game.py:249-257)
-  const int i0 = (vrot == 0) ? SIDE - 1 - hy : (vrot == 1) ? hx : (vrot == 2) ? hy : SIDE - 1 - hx;
+  // Recentring (game.py:249-251) and numpy.rot90 (game.py:257) are one affine map of the cell (y, x) to the output
+  // pixel p = i*N + j:  p = A*y + B*x + C with warp-uniform A, B, C; i0 = first output row of the board window.
+  int A, B, Cc, i0;
+  if (vrot == 0)      { A = N;  B = 1;  Cc = (SIDE - 1 - hy) * N + (SIDE - 1 - hx);             i0 = SIDE - 1 - hy; }
+  else if (vrot == 1) { A = 1;  B = -N; Cc = (N - SIDE + hx) * N + (SIDE - 1 - hy);             i0 = hx; }
+  else if (vrot == 2) { A = -N; B = -1; Cc = (N - SIDE + hy) * N + (N - SIDE + hx);             i0 = hy; }
+  else                { A = -1; B = N;  Cc = (SIDE - 1 - hx) * N + (N - SIDE + hy);             i0 = SIDE - 1 - hx; }
   const int W0 = i0 * 3 * N, W1 = W0 + E::WIN;
-  const int a = (int)((gidx0 + (size_t)W0) & 3);
-  const int off = (9 * a) % 12;             // off % 4 == a, off % 3 == 0
+  const int a0 = (int)(gidx0 & 3);              // misalignment of the plane's first float
+  const int a = (a0 + W0) & 3;
+  const int off = (9 * a) % 12;                 // off % 4 == a, off % 3 == 0
+  const int base3 = 3 * Cc - W0 + off;          // stage index of pixel p's channel 0 = 3*A*y + 3*B*x + base3
   float* stage = ctx.cur;
   // the bulk store that read this buffer two planes ago must have finished reading it
   if (lane == 0) bulk_wait_read<1>();
@@ -404,22 +414,15 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
     const float hv = __shfl_sync(kFull, my_hv, hsq < 0 ? 0 : hsq);
     int sidx = -1;
     if (c < CELLS) {
-      const int y = c / SIDE, x = c - y * SIDE;
-      const int gy = y - hy + (SIDE - 1), gx = x - hx + (SIDE - 1);
-      int i, j;
-      if (vrot == 0) { i = gy; j = gx; }
-      else if (vrot == 1) { i = N - 1 - gx; j = gy; }
-      else if (vrot == 2) { i = N - 1 - gy; j = N - 1 - gx; }
-      else { i = gx; j = N - 1 - gy; }
-      const int p = i * N + j;
+      const int y = cv.cy[q], x = cv.cx[q];
       float t0, t1, t2;
-      if (c == vhead) { t0 = t1 = t2 = -1.0f; }
+      if (c == vhead) { t0 = t1 = t2 = -1.0f; }                           // game.py:248
       else { t0 = (hsq >= 0) ? hv : 0.0f; t1 = cv.f1[q]; t2 = cv.food[q] ? foodv : 0.0f; }
       if (out != nullptr) {
-        sidx = 3 * p - W0 + off;
+        sidx = 3 * (A * y + B * x) + base3;
         stage[sidx] = t0; stage[sidx + 1] = t1; stage[sidx + 2] = t2;
       }
-      if (kWantKey) key_accumulate((uint32_t)p, __float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), k0, k1);
+      if (kWantKey) key_accumulate((uint32_t)(A * y + B * x + Cc), __float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), k0, k1);
     }
     ctx.prev_cur[q] = sidx;
   }
@@ -431,34 +434,25 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   if (out == nullptr) return;
   fence_proxy_async_smem();
   __syncwarp();
-  const size_t gA = (gidx0 + 3) & ~(size_t)3, gend = gidx0 + PLANE, gE = gend & ~(size_t)3;
-  const size_t gw0 = gidx0 + (size_t)W0, gw1 = gidx0 + (size_t)W1;
-  size_t GA = gw0 & ~(size_t)3, GE = (gw1 + 3) & ~(size_t)3;       // aligned cover of the window
-  if (GA < gA) GA = gA;
-  if (GE > gE) GE = gE;
+  // plane-relative element ranges (32-bit): [eA, eE) is the 16-byte aligned interior of the plane, [EA, EE) the aligned
+  // cover of the window clipped to it
+  const int eA = (4 - a0) & 3, eE = PLANE - ((a0 + PLANE) & 3);
+  int EA = W0 - a, EE = W1 + ((4 - ((a0 + W1) & 3)) & 3);
+  if (EA < eA) EA = eA;
+  if (EE > eE) EE = eE;
+  float* obase = out + gidx0;
   if (lane == 0) {
-    if (GA > gA) {                                                   // wall before the window
-      const int e_s = (int)(gA - gidx0);
-      bulk_s2g(out + gA, ctx.bg + 4 * (e_s % 3), (uint32_t)((GA - gA) * 4));
-    }
-    // window: plane element e sits at stage[e - W0 + off]
-    bulk_s2g(out + GA, stage + ((long long)(GA - gidx0) - W0 + off), (uint32_t)((GE - GA) * 4));
-    if (gE > GE) {                                                   // wall after the window
-      const int e_s = (int)(GE - gidx0);
-      bulk_s2g(out + GE, ctx.bg + 4 * (e_s % 3), (uint32_t)((gE - GE) * 4));
-    }
+    if (EA > eA) bulk_s2g(obase + eA, ctx.bg + 4 * (eA % 3), (uint32_t)((EA - eA) * 4));            // wall before the window
+    bulk_s2g(obase + EA, stage + (EA - W0 + off), (uint32_t)((EE - EA) * 4));                       // the window rows
+    if (eE > EE) bulk_s2g(obase + EE, ctx.bg + 4 * (EE % 3), (uint32_t)((eE - EE) * 4));            // wall after the window
     bulk_commit();
   } else if (lane <= 6) {
     // up to 3 floats before the first and after the last 16-byte boundary of the plane
-    const int k = lane - 1;                                          // 0..2 head, 3..5 tail
-    const int nhead = (int)(gA - gidx0), ntail = (int)(gend - gE);
+    const int k = lane - 1;                                                                          // 0..2 head, 3..5 tail
     int e = -1;
-    if (k < 3) { if (k < nhead) e = k; }
-    else if (k - 3 < ntail) e = (int)(gE - gidx0) + (k - 3);
-    if (e >= 0) {
-      const float v = (e >= W0 && e < W1) ? stage[e - W0 + off] : ((e % 3 == 1) ? 1.0f : 0.0f);
-      out[gidx0 + e] = v;
-    }
+    if (k < 3) { if (k < eA) e = k; }
+    else if (k - 3 < PLANE - eE) e = eE + (k - 3);
+    if (e >= 0) obase[e] = (e >= W0 && e < W1) ? stage[e - W0 + off] : ((e % 3 == 1) ? 1.0f : 0.0f);
   }
   ctx.cur = ctx.oth; ctx.oth = stage;
 #pragma unroll
