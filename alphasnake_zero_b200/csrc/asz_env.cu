@@ -32,6 +32,7 @@ struct EnvParams {
   const uint8_t* actions; const int32_t* spawn_cells;
   float* planes; int32_t* row_ids; uint64_t* keys; int max_rows; int32_t* row_count;
   uint8_t* ended; int8_t* rewards; unsigned long long* totals;
+  int* work_counter;   // dynamic game scheduler of the persistent kernel (zeroed before the launch)
 };
 
 // ---- record load / store ------------------------------------------------------------------------------------------
@@ -73,13 +74,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   using G = Geo<SIDE>;
   using E = EncGeo<G>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned long long s_tot[8];
   const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
   // smem: [per-CTA wall pattern][per warp: 2 staging buffers][per warp: board]
   float* s_bg = reinterpret_cast<float*>(smem_raw);
   float* stage0 = s_bg + E::BGLEN + warp * 2 * E::WSTAGE;
   uint16_t* sb = reinterpret_cast<uint16_t*>(s_bg + E::BGLEN + WARPS * 2 * E::WSTAGE) + warp * G::PC;
-  if (threadIdx.x < 8) s_tot[threadIdx.x] = 0ull;
   const bool enc = (p.flags & ASZ_STEP_ENCODE) != 0;
   if (enc) {
     fill_wall_pattern(s_bg, E::BGLEN, (int)threadIdx.x, WARPS * 32);
@@ -91,14 +90,39 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg;
 #pragma unroll
   for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
-  unsigned long long t_tics = 0, t_planes = 0;   // lane 0 accumulates, flushed once per warp
+  __shared__ uint32_t s_wtot[WARPS][12];         // per-warp totals (only lane 0 of the warp touches its row)
+  if (lane < 12) s_wtot[warp][lane] = 0u;
+  __syncwarp();
 
+  // dynamic scheduling: the first game of a warp is static, later ones come from a global counter that is fetched one
+  // game ahead; the next game's record is prefetched into registers while the current game's planes are encoded
   const int n_warps = (int)gridDim.x * WARPS;
-  for (int g = (int)blockIdx.x * WARPS + warp; g < p.G; g += n_warps) {
-    load_board<G>(p.cells + (size_t)g * G::PC, sb, lane);
+  constexpr int BW = G::CPL / 2;                 // 32-bit words of board per lane
+  uint32_t pf_board[BW];
+  uint64_t pf_snake = 0;
+  uint32_t pf_meta = 0;
+  int g = (int)blockIdx.x * WARPS + warp;
+  auto prefetch = [&](int gi) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cells + (size_t)gi * G::PC);
+#pragma unroll
+    for (int q = 0; q < BW; ++q) pf_board[q] = src[lane * BW + q];
+    if (lane < 8) { pf_snake = p.snakes[(size_t)gi * 8 + lane]; pf_meta = p.meta[(size_t)gi * 8 + lane]; }
+  };
+  if (g < p.G) prefetch(g);
+  while (g < p.G) {
+    int nxt = 0;
+    if (lane == 0) nxt = n_warps + atomicAdd(p.work_counter, 1);
+    {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sb);
+#pragma unroll
+      for (int q = 0; q < BW; ++q) dst[lane * BW + q] = pf_board[q];
+    }
     Snake sn; sn.head = 0xFFFF; sn.len = 0; sn.health = 0; sn.last = 0; sn.alive = 0; sn.reward = 0;
-    if (lane < 8) sn = unpack_snake(p.snakes[(size_t)g * 8 + lane]);
-    Meta m = load_meta(p.meta + (size_t)g * 8, lane);
+    if (lane < 8) sn = unpack_snake(pf_snake);
+    Meta m;
+    m.turn = __shfl_sync(kFull, pf_meta, 0); m.episode = __shfl_sync(kFull, pf_meta, 1); m.wall = __shfl_sync(kFull, pf_meta, 2);
+    m.body = __shfl_sync(kFull, pf_meta, 3); m.headc = __shfl_sync(kFull, pf_meta, 4); m.starve = __shfl_sync(kFull, pf_meta, 5);
+    m.eaten = __shfl_sync(kFull, pf_meta, 6); m.flags = __shfl_sync(kFull, pf_meta, 7);
     __syncwarp();
     if ((p.flags & ASZ_STEP_TIC) && !(m.flags & 1u)) {
       int move = 1;
@@ -117,41 +141,44 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         p.rewards[(size_t)g * 8 + lane] = (int8_t)(sn.reward == 1 ? 1 : sn.reward == 2 ? -1 : 0);
       if (lane == 0) {
         if (p.ended != nullptr) p.ended[g] = r.ended ? 1 : 0;
-        t_tics += 1;
+        s_wtot[warp][7] += 1u;
         if (r.ended) {   // mp_game_runner.py:56-61
-          atomicAdd(&s_tot[0], (unsigned long long)m.wall); atomicAdd(&s_tot[1], (unsigned long long)m.body);
-          atomicAdd(&s_tot[2], (unsigned long long)m.headc); atomicAdd(&s_tot[3], (unsigned long long)m.starve);
-          atomicAdd(&s_tot[4], (unsigned long long)m.eaten); atomicAdd(&s_tot[5], (unsigned long long)m.turn);
-          atomicAdd(&s_tot[6], 1ull);
+          s_wtot[warp][0] += m.wall; s_wtot[warp][1] += m.body; s_wtot[warp][2] += m.headc; s_wtot[warp][3] += m.starve;
+          s_wtot[warp][4] += m.eaten; s_wtot[warp][5] += m.turn; s_wtot[warp][6] += 1u;
         }
       }
       if (r.ended && (p.flags & ASZ_STEP_AUTO_RESET)) warp_init_native<G>(sb, sn, m, p.S, p.seed, (uint32_t)g, m.episode + 1);
       // write the record back
-      uint16_t* gc = p.cells + (size_t)g * G::PC;
-      if constexpr (G::CPL % 4 == 0) {
+      {
+        uint32_t* gc = reinterpret_cast<uint32_t*>(p.cells + (size_t)g * G::PC);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(sb);
+        if constexpr (BW % 2 == 0) {
 #pragma unroll
-        for (int q = 0; q < G::CPL / 4; ++q)
-          reinterpret_cast<uint2*>(gc)[lane * (G::CPL / 4) + q] = reinterpret_cast<const uint2*>(sb)[lane * (G::CPL / 4) + q];
-      } else {
+          for (int q = 0; q < BW / 2; ++q)
+            reinterpret_cast<uint2*>(gc)[lane * (BW / 2) + q] = reinterpret_cast<const uint2*>(src)[lane * (BW / 2) + q];
+        } else {
 #pragma unroll
-        for (int q = 0; q < G::CPL / 2; ++q)
-          reinterpret_cast<uint32_t*>(gc)[lane * (G::CPL / 2) + q] = reinterpret_cast<const uint32_t*>(sb)[lane * (G::CPL / 2) + q];
+          for (int q = 0; q < BW; ++q) gc[lane * BW + q] = src[lane * BW + q];
+        }
       }
       if (lane < 8) p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
       store_meta(p.meta + (size_t)g * 8, m, lane);
     } else if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) {
       p.ended[g] = 0;
     }
+    // the next game's record streams in while this game's planes are encoded
+    nxt = __shfl_sync(kFull, nxt, 0);
+    if (nxt < p.G) prefetch(nxt);
     // ---- rows of this game: one atomicAdd per warp (rows of a game stay contiguous, ascending snake id) ----
     if (enc && !(m.flags & 1u)) {
       const unsigned live_mask = __ballot_sync(kFull, sn.alive != 0);
       const int n_rows = __popc(live_mask);
       if (n_rows > 0) {
         int row = 0;
-        if (lane == 0) { row = atomicAdd(p.row_count, n_rows); t_planes += (unsigned long long)n_rows; }
-        row = __shfl_sync(kFull, row, 0);
+        if (lane == 0) { row = atomicAdd(p.row_count, n_rows); s_wtot[warp][8] += (uint32_t)n_rows; }
         CellView<G> cv;
         warp_cell_view<G>(sb, sn, cv);
+        row = __shfl_sync(kFull, row, 0);
         unsigned rest = live_mask;
         while (rest) {
           const int vs = __ffs(rest) - 1;
@@ -171,14 +198,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       }
     }
     __syncwarp();   // the board buffer is reused by the next game
+    g = nxt;
   }
   if (lane == 0) {
     bulk_wait_read<0>();   // shared memory must stay valid until the copy engine has read it
-    if (t_tics) atomicAdd(&s_tot[7], t_tics);
-    if (t_planes) atomicAdd(&p.totals[8], t_planes);
   }
-  __syncthreads();
-  if (threadIdx.x < 8 && s_tot[threadIdx.x] != 0ull) atomicAdd(&p.totals[threadIdx.x], s_tot[threadIdx.x]);
+  __syncwarp();
+  if (lane < 9 && s_wtot[warp][lane] != 0u) atomicAdd(&p.totals[lane], (unsigned long long)s_wtot[warp][lane]);
 }
 
 // ---- reset kernel ---------------------------------------------------------------------------------------------------
@@ -290,7 +316,7 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
   if (rc != ASZ_OK) { delete e; return rc; }
   ASZ_CUDA(cudaMalloc(&e->planes, rows * (size_t)e->plane * sizeof(float) + 16));
   ASZ_CUDA(cudaMalloc(&e->row_ids, rows * sizeof(int32_t)));
-  ASZ_CUDA(cudaMalloc(&e->row_count, sizeof(int32_t)));
+  ASZ_CUDA(cudaMalloc(&e->row_count, 2 * sizeof(int32_t)));   // [0] rows of the last step, [1] work counter
   ASZ_CUDA(cudaMalloc(&e->actions, G * 8));
   ASZ_CUDA(cudaMalloc(&e->spawn_cells, G * sizeof(int32_t)));
   ASZ_CUDA(cudaMalloc(&e->ended, G));
@@ -348,7 +374,9 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.planes = a->d_planes; p.row_ids = a->d_row_ids; p.keys = a->d_keys; p.max_rows = a->max_rows;
   p.row_count = a->d_row_count ? a->d_row_count : e->row_count;
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals;
-  ASZ_CUDA(cudaMemsetAsync(p.row_count, 0, sizeof(int32_t), st));
+  p.work_counter = e->row_count + 1;
+  ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, 2 * sizeof(int32_t), st));
+  if (p.row_count != e->row_count) ASZ_CUDA(cudaMemsetAsync(p.row_count, 0, sizeof(int32_t), st));
   switch (e->cfg.side) {
     case 7: return EnvLaunch<7>::step(p, st);
     case 11: return EnvLaunch<11>::step(p, st);

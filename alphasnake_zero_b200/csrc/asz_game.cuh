@@ -449,10 +449,14 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   } else if (lane <= 6) {
     // up to 3 floats before the first and after the last 16-byte boundary of the plane
     const int k = lane - 1;                                                                          // 0..2 head, 3..5 tail
-    int e = -1;
-    if (k < 3) { if (k < eA) e = k; }
-    else if (k - 3 < PLANE - eE) e = eE + (k - 3);
-    if (e >= 0) obase[e] = (e >= W0 && e < W1) ? stage[e - W0 + off] : ((e % 3 == 1) ? 1.0f : 0.0f);
+    const bool is_head = k < 3;
+    const int e = is_head ? k : eE + (k - 3);
+    const bool on = is_head ? (k < eA) : (e < PLANE);
+    if (on) {
+      // PLANE % 3 == 0 and eE = PLANE - (0..3): the phase of a tail element follows from its distance to the end
+      const int ph = is_head ? k : (3 - (PLANE - e)) % 3;
+      obase[e] = (e >= W0 && e < W1) ? stage[e - W0 + off] : ((ph == 1) ? 1.0f : 0.0f);
+    }
   }
   ctx.cur = ctx.oth; ctx.oth = stage;
 #pragma unroll
