@@ -253,6 +253,28 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = e0.elapsed_time(e1)
     e2e_steps_local = eng.totals()["tics"] - t_b["tics"]
 
+    # ---- leg 3: self-play (search + value network) on every rank ------------------------------------------------------
+    sp = {}
+    if not args.no_selfplay:
+        for key, use_net in (("mcts", True), ("mcts_search_only", False)):
+            try:
+                barrier()
+                r = selfplay_leg(rank, args.sp_games, 100, 8, args.sp_turns, 1, use_net=use_net)
+                if world > 1:   # whole-job aggregate: sum of the work of all ranks / slowest rank's time
+                    rates = ("sims_per_sec", "node_visits_per_sec", "nn_evals_per_sec", "subgame_tics_per_sec")
+                    t = torch.tensor([r["seconds"]] + [r[k] * r["seconds"] for k in rates], dtype=torch.float64, device=dev)
+                    mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                    sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+                    r["seconds"] = float(mx[0])
+                    for i, k in enumerate(rates):
+                        r[k] = float(sm[1 + i]) / float(mx[0])
+                    if "net_tflops" in r:
+                        r["net_tflops_all_gpus"] = r["nn_evals_per_sec"] * 1043724288 / 1e12
+                    r["aggregate_over_gpus"] = world
+                sp[key] = r
+            except Exception as ex:   # the headline line must still be printed
+                sp[key] = {"error": repr(ex)}
+
     # ---- reduce over ranks: max time, sum of work ----------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -296,12 +318,7 @@ def run_ours(args, rank, world, local_rank):
                 "note": "asz_env_step_host: pinned host actions in, per-game ended/rewards + row count out; planes stay in HBM for the network"},
         "gpu_launches": K, "clocks": clocks,
     }
-    if not args.no_selfplay:
-        try:
-            out["mcts"] = selfplay_leg(rank, args.sp_games, 100, 8, args.sp_turns, 1, use_net=True)
-            out["mcts_search_only"] = selfplay_leg(rank, args.sp_games, 100, 8, args.sp_turns, 1, use_net=False)
-        except Exception as ex:   # the headline line must still be printed
-            out["mcts"] = {"error": repr(ex)}
+    out.update(sp)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
