@@ -276,34 +276,40 @@ template <int HALO>
 struct PersistSmem {
   static constexpr int kSuper = 256;
   static constexpr int rows = kSuper + 2 * HALO;
-  static constexpr size_t a_bytes = (size_t)kKC * rows * 16;
-  static constexpr size_t b_chunk = (size_t)8 * kC * 16;     // half a tap
-  static constexpr int b_stages = 3;
-  static constexpr size_t total = 2 * a_bytes + b_stages * b_chunk + 3 * kC * sizeof(float) + 16 * sizeof(uint64_t) + 64;
+  static constexpr size_t a_bytes = (size_t)kKC * rows * 16;      // one halo tile, managed as two channel halves
+  static constexpr size_t b_chunk = (size_t)8 * kC * 16;          // half a tap = 16 KB
+  static constexpr size_t tail = 3 * kC * sizeof(float) + 40 * sizeof(uint64_t) + 64;
+  static constexpr int b_stages = (int)((232448 - a_bytes - tail) / b_chunk);   // 9 at HALO 24, 8 at HALO 40
+  static constexpr size_t total = a_bytes + b_stages * b_chunk + tail;
 };
 
+// Loop order inside a super-tile: channel half c (8 of the 16 chunks) outermost, then the 9 taps.  The A half c is
+// released as soon as its 9 taps are issued, so the next super-tile's half 0 streams in while half 1 is being consumed
+// (and vice versa): the halo tile is effectively double buffered at 1x its size, which leaves room for 8-9 weight
+// stages -- enough chunks in flight to cover the L2 latency of the weight stream.
 template <int HALO>
 __global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p, int n_super) {
   using SM = PersistSmem<HALO>;
+  constexpr int NS = SM::b_stages;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
-  unsigned char* sB = smem + 2 * SM::a_bytes;
-  float* s_scale = reinterpret_cast<float*>(sB + SM::b_stages * SM::b_chunk);
+  unsigned char* sB = smem + SM::a_bytes;
+  float* s_scale = reinterpret_cast<float*>(sB + NS * SM::b_chunk);
   float* s_bias = s_scale + kC;
   float* s_head = s_bias + kC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_head + kC);
-  uint64_t* a_full = bars;          // [2]
-  uint64_t* a_empty = bars + 2;     // [2]
-  uint64_t* b_full = bars + 4;      // [3]
-  uint64_t* b_empty = bars + 7;     // [3]
-  uint64_t* acc_full = bars + 10;   // [2]
-  uint64_t* acc_empty = bars + 12;  // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* a_full = bars;             // [2] channel halves
+  uint64_t* a_empty = bars + 2;        // [2]
+  uint64_t* acc_full = bars + 4;       // [2] accumulator pairs
+  uint64_t* acc_empty = bars + 6;      // [2]
+  uint64_t* b_full = bars + 8;         // [NS]
+  uint64_t* b_empty = bars + 8 + NS;   // [NS]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NS);
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
   const int kc_in = p.kc_in, taps = p.taps;
-  const int kc_chunk = kc_in < 8 ? kc_in : 8;
-  const int chunks_per_tap = kc_in / kc_chunk;
-  const uint32_t chunk_bytes = (uint32_t)(kc_chunk * kC * 16);
+  const int kc_half = kc_in < 8 ? kc_in : 8;
+  const int halves = kc_in / kc_half;
+  const uint32_t chunk_bytes = (uint32_t)(kc_half * kC * 16);
 
   for (int i = (int)threadIdx.x; i < kC; i += (int)blockDim.x) {
     s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i];
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
-    for (int i = 0; i < SM::b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -322,47 +328,46 @@ __global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t bit = 0;   // weight-chunk counter
-      uint32_t it = 0;    // super-tile counter of this CTA
+      uint32_t bit = 0, it = 0;
       for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
-        const int buf = (int)(it & 1u);
-        mbar_wait(&a_empty[buf], ((it >> 1) & 1u) ^ 1u);
         const size_t row0 = (size_t)kGuard + (size_t)st * SM::kSuper - HALO;
-        mbar_expect_tx(&a_full[buf], (uint32_t)(kc_in * SM::rows * 16));
-        for (int kc = 0; kc < kc_in; ++kc)
-          bulk_g2s(sA + buf * SM::a_bytes + (size_t)kc * SM::rows * 16, p.in + ((size_t)kc * p.P_tot + row0) * 8, SM::rows * 16, &a_full[buf]);
-        for (int t = 0; t < taps; ++t)
-          for (int c = 0; c < chunks_per_tap; ++c, ++bit) {
-            const int s = (int)(bit % SM::b_stages);
-            mbar_wait(&b_empty[s], ((bit / SM::b_stages) & 1u) ^ 1u);
-            mbar_expect_tx(&b_full[s], chunk_bytes);
-            bulk_g2s(sB + (size_t)s * SM::b_chunk, p.wt + ((size_t)t * kc_in + (size_t)c * kc_chunk) * kC * 8, chunk_bytes, &b_full[s]);
+        for (int c = 0; c < halves; ++c) {
+          mbar_wait(&a_empty[c], (it & 1u) ^ 1u);
+          mbar_expect_tx(&a_full[c], (uint32_t)(kc_half * SM::rows * 16));
+          for (int k = 0; k < kc_half; ++k) {
+            const int kc = c * kc_half + k;
+            bulk_g2s(sA + (size_t)kc * SM::rows * 16, p.in + ((size_t)kc * p.P_tot + row0) * 8, SM::rows * 16, &a_full[c]);
           }
+          for (int t = 0; t < taps; ++t, ++bit) {
+            const int s = (int)(bit % NS);
+            mbar_wait(&b_empty[s], ((bit / NS) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[s], chunk_bytes);
+            bulk_g2s(sB + (size_t)s * SM::b_chunk, p.wt + ((size_t)t * kc_in + (size_t)c * kc_half) * kC * 8, chunk_bytes, &b_full[s]);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t bit = 0, it = 0;
-      const uint32_t a_base0 = smem_u32(sA), b_base = smem_u32(sB);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
         const int buf = (int)(it & 1u);
-        const uint32_t ph = (it >> 1) & 1u;
-        mbar_wait(&acc_empty[buf], ph ^ 1u);     // the epilogue has drained this accumulator pair
-        mbar_wait(&a_full[buf], ph);
-        tc_fence_after();
-        const uint32_t a_base = a_base0 + (uint32_t)(buf * SM::a_bytes);
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator pair
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
         uint32_t first = 1;
-        for (int t = 0; t < taps; ++t) {
-          const int shift = (taps == 1) ? 0 : ((t / 3) - 1) * p.pitch + ((t % 3) - 1);
-          for (int c = 0; c < chunks_per_tap; ++c, ++bit) {
-            const int s = (int)(bit % SM::b_stages);
-            mbar_wait(&b_full[s], (bit / SM::b_stages) & 1u);
+        for (int c = 0; c < halves; ++c) {
+          mbar_wait(&a_full[c], it & 1u);
+          tc_fence_after();
+          for (int t = 0; t < taps; ++t, ++bit) {
+            const int shift = (taps == 1) ? 0 : ((t / 3) - 1) * p.pitch + ((t % 3) - 1);
+            const int s = (int)(bit % NS);
+            mbar_wait(&b_full[s], (bit / NS) & 1u);
             tc_fence_after();
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-              for (int ks = 0; ks < kc_chunk / 2; ++ks) {
-                const int kc = c * kc_chunk + 2 * ks;
+              for (int ks = 0; ks < kc_half / 2; ++ks) {
+                const int kc = c * kc_half + 2 * ks;
                 const uint32_t a_addr = a_base + (uint32_t)((kc * SM::rows + HALO + shift + sub * kTileM) * 16);
                 const uint32_t b_addr = b_base + (uint32_t)(s * SM::b_chunk) + (uint32_t)((2 * ks) * kC * 16);
                 umma_bf16(tmem_d + (uint32_t)(sub * kC), smem_desc(a_addr, SM::rows * 16, 128), smem_desc(b_addr, kC * 16, 128), kIdesc,
@@ -372,9 +377,9 @@ __global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p
             first = 0;
             umma_commit(&b_empty[s]);
           }
+          umma_commit(&a_empty[c]);      // this channel half of the halo tile may be overwritten by the next super-tile
         }
         umma_commit(&acc_full[buf]);
-        umma_commit(&a_empty[buf]);
       }
     }
   } else {
