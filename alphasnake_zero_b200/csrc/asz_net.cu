@@ -288,7 +288,7 @@ struct PersistSmem {
 // (and vice versa): the halo tile is effectively double buffered at 1x its size, which leaves room for 8-9 weight
 // stages -- enough chunks in flight to cover the L2 latency of the weight stream.
 template <int HALO>
-__global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p, int n_super) {
+__global__ void __launch_bounds__(320, 1) conv_persist_kernel(const ConvParams p, int n_super) {
   using SM = PersistSmem<HALO>;
   constexpr int NS = SM::b_stages;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p
     s_head[i] = p.head_w ? p.head_w[i] : 0.0f;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < NS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     fence_barrier_init();
   }
@@ -383,57 +383,58 @@ __global__ void __launch_bounds__(192, 1) conv_persist_kernel(const ConvParams p
       }
     }
   } else {
+    // 8 epilogue warps: warps 2..5 take rows 0..127 of the super-tile (sub 0), warps 6..9 rows 128..255 (sub 1);
+    // a warp may only touch the TMEM lane quarter warp % 4.  One thread = one output row (position), 128 channels.
     const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
     uint32_t it = 0;
     for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
       const int buf = (int)(it & 1u);
+      const int pos = st * SM::kSuper + sub * kTileM + q * 32 + lane;
+      const int rem = pos % p.img_stride;
+      const int y = rem / p.pitch, x = rem - y * p.pitch;
+      const bool valid = pos < p.P_real && y < p.real && x < p.real;
+      const size_t grow = (size_t)kGuard + (size_t)pos;
+      // the residual row does not depend on the accumulator: fetch it while the MMAs of this super-tile run
+      uint4 rv[kKC];
+      if (p.res != nullptr) {
+#pragma unroll
+        for (int kc = 0; kc < kKC; ++kc) rv[kc] = *reinterpret_cast<const uint4*>(p.res + ((size_t)kc * p.P_tot + grow) * 8);
+      }
       mbar_wait(&acc_full[buf], (it >> 1) & 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const int pos = st * SM::kSuper + sub * kTileM + q * 32 + lane;
-        const int rem = pos % p.img_stride;
-        const int y = rem / p.pitch, x = rem - y * p.pitch;
-        const bool valid = pos < p.P_real && y < p.real && x < p.real;
-        const size_t grow = (size_t)kGuard + (size_t)pos;
-        float head_acc = 0.0f;
-#pragma unroll 1
-        for (int cb = 0; cb < kC / 32; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (uint32_t)(buf * 256 + sub * kC + cb * 32) + ((uint32_t)(q * 32) << 16), v);
-          uint4 rv[4];
-          if (p.res != nullptr) {
+      float head_acc = 0.0f;
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) rv[j8] = *reinterpret_cast<const uint4*>(p.res + ((size_t)(cb * 4 + j8) * p.P_tot + grow) * 8);
+      for (int cb = 0; cb < kC / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t)(buf * 256 + sub * kC + cb * 32) + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int kc = cb * 4 + j8;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * s_scale[kc * 8 + j] + s_bias[kc * 8 + j];
+          if (p.res != nullptr) {
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[kc]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 t2 = __bfloat1622float2(rb[j]); f[2 * j] += t2.x; f[2 * j + 1] += t2.y; }
           }
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const int kc = cb * 4 + j8;
-            float f[8];
+          for (int j = 0; j < 8; ++j) f[j] = valid ? fmaxf(f[j], 0.0f) : 0.0f;
+          if (p.out != nullptr) {
+            uint4 ov;
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * s_scale[kc * 8 + j] + s_bias[kc * 8 + j];
-            if (p.res != nullptr) {
-              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[j8]);
+            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>(p.out + ((size_t)kc * p.P_tot + grow) * 8) = ov;
+          }
+          if (p.head_out != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 t2 = __bfloat1622float2(rb[j]); f[2 * j] += t2.x; f[2 * j + 1] += t2.y; }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = valid ? fmaxf(f[j], 0.0f) : 0.0f;
-            if (p.out != nullptr) {
-              uint4 ov;
-              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              *reinterpret_cast<uint4*>(p.out + ((size_t)kc * p.P_tot + grow) * 8) = ov;
-            }
-            if (p.head_out != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) head_acc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), s_head[kc * 8 + j], head_acc);
-            }
+            for (int j = 0; j < 8; ++j) head_acc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), s_head[kc * 8 + j], head_acc);
           }
         }
-        if (p.head_out != nullptr) p.head_out[grow] = valid ? fmaxf(head_acc * p.head_scale + p.head_bias, 0.0f) : 0.0f;
       }
+      if (p.head_out != nullptr) p.head_out[grow] = valid ? fmaxf(head_acc * p.head_scale + p.head_bias, 0.0f) : 0.0f;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -582,8 +583,8 @@ static int launch_conv(asz_net* n, int layer, const __nv_bfloat16* in, const __n
   }
   const int n_super = (p.P_real + 255) / 256;
   const int grid = std::min(n_super, n->n_sm);
-  if (n->pitch + 1 <= 24) conv_persist_kernel<24><<<grid, 192, PersistSmem<24>::total, st>>>(p, n_super);
-  else conv_persist_kernel<40><<<grid, 192, PersistSmem<40>::total, st>>>(p, n_super);
+  if (n->pitch + 1 <= 24) conv_persist_kernel<24><<<grid, 320, PersistSmem<24>::total, st>>>(p, n_super);
+  else conv_persist_kernel<40><<<grid, 320, PersistSmem<40>::total, st>>>(p, n_super);
   return cuda_ok(cudaGetLastError(), "conv_persist_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
 }
 
