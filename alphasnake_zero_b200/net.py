@@ -34,7 +34,7 @@ def _conv0_layout(k):
 
 class NativeNet:
 
-    def __init__(self, weights, device, chunk_images=1024):
+    def __init__(self, weights, device, chunk_images=4096):
         if not torch.cuda.is_available():
             raise _lib.AszError("no CUDA device: the native network has no CPU fallback")
         self.device = torch.device(device)
