@@ -430,6 +430,18 @@ __global__ void obstacle_mask_kernel(const float* planes, int n, int side, int n
   }
 }
 
+// test hook: softermax + inverse-CDF draw + argmaxs on arbitrary rows (agent.py:114-137, numpy.random.choice)
+__global__ void policy_debug_kernel(const float* z, const double* u, int n, float base, float* pmf, int32_t* choice, int32_t* amax) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  const float q[3] = {z[3 * i], z[3 * i + 1], z[3 * i + 2]};
+  float p[3];
+  softermax3(q, base, p);
+  pmf[3 * i] = p[0]; pmf[3 * i + 1] = p[1]; pmf[3 * i + 2] = p[2];
+  choice[i] = choice3(p, u[i]);
+  amax[i] = argmax3(q);
+}
+
 // ---- table maintenance --------------------------------------------------------------------------------------------
 __global__ void table_rebuild_kernel(const Table src, Table dst, uint32_t cur_turn, int D, unsigned long long* occupied) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -668,6 +680,14 @@ int asz_obstacle_mask(asz_engine* e, const float* d_planes, int32_t n, float* d_
   if (n <= 0) return ASZ_OK;
   obstacle_mask_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_planes, n, e->cfg.side, e->cfg.numpy1_mask, d_values);
   return cuda_ok(cudaGetLastError(), "obstacle_mask_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
+}
+
+int asz_debug_policy(const float* d_z, const double* d_u, int32_t n, float base, float* d_pmf, int32_t* d_choice, int32_t* d_argmax,
+                     void* stream) {
+  if (!d_z || !d_u || !d_pmf || !d_choice || !d_argmax) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if (n <= 0) return ASZ_OK;
+  policy_debug_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_z, d_u, n, base, d_pmf, d_choice, d_argmax);
+  return cuda_ok(cudaGetLastError(), "policy_debug_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
 }
 
 int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_q, uint8_t* d_root_moves, void* stream) {

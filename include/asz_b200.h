@@ -166,6 +166,10 @@ int asz_search_stub_values(asz_engine* e, void* stream);
 int asz_search_run_stub(asz_engine* e, uint8_t* d_trace, int32_t trace_mode, const uint8_t* d_root_trace, void* stream);
 /* AlphaNNet.v's obstacle mask (alpha_nnet.py:63-76) applied in place to d_values [n][3] for d_planes [n][plane] */
 int asz_obstacle_mask(asz_engine* e, const float* d_planes, int32_t n, float* d_values, void* stream);
+/* test hook: Agent.softermax (agent.py:114-122), numpy.random.choice([0,1,2], p) for a given uniform draw u (float64),
+ * and Agent.argmaxs (agent.py:124-137) on n rows of 3 values; all DEVICE pointers */
+int asz_debug_policy(const float* d_z, const double* d_u, int32_t n, float base, float* d_pmf, int32_t* d_choice,
+                     int32_t* d_argmax, void* stream);
 /* Agent.clear (agent.py:140-147): drops the table */
 int asz_search_clear(asz_engine* e, void* stream);
 /* h_info[8] = P (sub-games per root game), epochs, max steps, sub-games, max eval rows, table log2 capacity, root turn, epoch */

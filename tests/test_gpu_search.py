@@ -145,3 +145,104 @@ def test_native_search_against_oracle(side, S, G, D, breadth, base, training, tu
         for g_i in range(0, G, 5):
             assert_dump_equal(eng.get_state(g_i), games[g_i].dump(), "root game %d after turn %d" % (g_i, t))
     eng.close()
+
+
+def test_policy_functions_against_reference():
+    """softermax / numpy.random.choice / argmaxs kernels against known answers recorded from the reference"""
+    import ctypes as C
+    import torch
+    from alphasnake_zero_b200 import _lib
+    z = load("funcs.npz")
+    Z = torch.from_numpy(z["Z"]).cuda()
+    u = torch.from_numpy(z["choice_u"]).cuda()
+    n = Z.shape[0]
+    L = _lib.lib()
+    for base in (2, 3, 10, 100):
+        pmf = torch.zeros(n, 3, device="cuda"); ch = torch.zeros(n, dtype=torch.int32, device="cuda"); am = torch.zeros_like(ch)
+        _lib.check(L.asz_debug_policy(C.c_void_p(Z.data_ptr()), C.c_void_p(u.data_ptr()), n, float(base), C.c_void_p(pmf.data_ptr()),
+                                      C.c_void_p(ch.data_ptr()), C.c_void_p(am.data_ptr()), None))
+        torch.cuda.synchronize()
+        want = z["softermax_%d" % base]
+        np.testing.assert_allclose(pmf.cpu().numpy(), want, rtol=4e-6, atol=1e-7)    # CUDA powf/atanhf vs NumPy: a few ulp
+        assert np.array_equal(am.cpu().numpy(), z["argmaxs"])
+        if base == 2:
+            # the draw is a function of (pmf, u); it may only differ where u sits within rounding of a cdf boundary
+            cdf = np.cumsum(want.astype(np.float64), axis=1); cdf /= cdf[:, -1:]
+            safe = np.abs(cdf[:, :2] - z["choice_u"][:, None]).min(axis=1) > 1e-5
+            assert np.array_equal(ch.cpu().numpy()[safe], z["choice_idx"][safe]) and safe.sum() > 200
+
+
+def test_obstacle_mask_kernel():
+    import ctypes as C
+    import torch
+    from oracle import oracle as orc
+    from alphasnake_zero_b200 import _lib
+    from tests.test_gpu_net import game_planes
+    X = game_planes(11, 4, 200, seed=5)
+    for numpy1 in (False, True):
+        eng = _engine(side=11, snakes=4, games=1, numpy1_mask=numpy1)
+        v = torch.full((len(X), 3), 0.25, device="cuda")
+        xs = torch.from_numpy(X).cuda()
+        _lib.check(eng.L.asz_obstacle_mask(eng.h, C.c_void_p(xs.data_ptr()), len(X), C.c_void_p(v.data_ptr()), None))
+        got = v.cpu().numpy()
+        c = 10
+        for i in range(len(X)):
+            b = [X[i, c, c - 1, 1], X[i, c - 1, c, 1], X[i, c, c + 1, 1]]
+            want = [(-1.0 if ((float(x) >= 0.04) if numpy1 else (x >= np.float32(0.04))) else 0.25) for x in b]
+            assert got[i].tolist() == want
+            if not numpy1:
+                assert np.array_equal(got[i], orc.obstacle_mask(X[i], 11, 11, np.full(3, 0.25, np.float32)))
+        eng.close()
+    # the two semantics differ exactly on dist == 2 cells (SURVEY.md D-11)
+    assert np.float32(2 * 0.02) >= np.float32(0.04) and not (float(np.float32(2 * 0.02)) >= 0.04)
+
+
+def test_search_with_network_value_function_against_oracle():
+    """the full Agent.make_moves path with a real value network: the engine calls the network on its eval batch, the
+    oracle calls the same network through its value-function hook; moves are recorded by the GPU and replayed."""
+    import torch
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    from oracle import oracle as orc
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = AlphaNNet(input_shape=(21, 21, 3), seed=4, backend="torch", dtype="fp32")
+    for k in ("dense2_w",):
+        net.weights[k] = (net.weights[k] * 30).astype(np.float32)      # spread the values so that the search discriminates
+
+    def vf_device(planes):
+        return net.forward_torch(planes, torch.float32)
+
+    def vf_host(planes):        # AlphaNNet.v contract: forward + obstacle mask
+        return net.v(planes)
+    G, S, D, B, seed = 6, 4, 8, 16, 31
+    eng = _engine(side=11, snakes=S, games=G, seed=seed, max_depth=D, max_breadth=B, softmax_base=2.0, training=True, table_log2=18)
+    eng.reset()
+    info = eng.search_info()
+    games = []
+    for gi in range(G):
+        g = orc.OracleGame(11, 11, S, 1); g.init_native(seed, gi, 0); g.set_ids(gi, 0); games.append(g)
+    agent = orc.OracleAgent(base=2.0, training=True, max_depth=D, max_breadth=B, value_fn=vf_host)
+    for t in range(2):
+        tree = torch.full((info["epochs"], info["max_steps"], G * info["P"], S), 255, dtype=torch.uint8, device="cuda")
+        q, mv = eng.search(value_fn=vf_device, trace=tree, trace_mode=2)
+        mvh = mv.cpu().numpy()
+        ids = [(gi, s) for gi in range(G) for s in games[gi].live_ids()]
+        root = np.array([mvh[g, s] for g, s in ids], np.uint8)
+        omv, oq = agent.make_moves(games, G, root_turn=t, tree_moves=np.ascontiguousarray(tree.cpu().numpy()), root_moves=root.copy(), replay=True)
+        tab, otab = eng.table(), agent.table()
+        oo = np.lexsort((otab["keys"][:, 1], otab["keys"][:, 0]))
+        assert np.array_equal(tab["keys"], otab["keys"][oo]) and np.array_equal(tab["N"], otab["N"][oo])
+        np.testing.assert_allclose(tab["W"], otab["W"][oo], rtol=0, atol=2e-4)
+        got_q = np.array([q.cpu().numpy()[g, s] for g, s in ids])
+        np.testing.assert_allclose(got_q, oq, rtol=0, atol=2e-5)
+        assert np.abs(oq[oq > -1]).max() > 0.01
+        actions = np.ones((G, 8), np.uint8)
+        for (g, s), m in zip(ids, root):
+            actions[g, s] = m
+        eng.step(actions=torch.from_numpy(actions).cuda(), spawn_mode=2, tic=True, encode=False)
+        r0 = 0
+        for gi in range(G):
+            n = games[gi].n_live
+            games[gi].tic(root[r0:r0 + n].astype(np.int32), spawn_mode=2, chance=0.15, seed=seed)
+            r0 += n
+    eng.close()
