@@ -151,6 +151,27 @@ def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True):
     return out
 
 
+def cpu_selfplay_baseline(games=8, breadth=50, depth=8):
+    """configs[0] of BASELINE.json on the host cores, bounded: the C port of the reference's search with a torch-CPU fp32
+    network of identical architecture as AlphaNNet.v (TensorFlow is not installable here).  One root turn."""
+    import numpy as np
+    import torch
+    from oracle import oracle as orc
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    net = AlphaNNet(input_shape=(2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0, backend="torch", dtype="fp32", device="cpu")
+    gs = []
+    for gi in range(games):
+        g = orc.OracleGame(SIDE, SIDE, SNAKES, HEALTH_DEC); g.init_native(0, gi, 0); g.set_ids(gi, 0); gs.append(g)
+    agent = orc.OracleAgent(base=2.0, training=True, max_depth=depth, max_breadth=breadth, value_fn=lambda X: net.v(np.array(X)))
+    t0 = time.time()
+    agent.make_moves(gs, games, root_turn=0, seed=0)
+    dt = time.time() - t0
+    return {"sims_per_sec": agent.stat("subgames") / dt, "node_visits_per_sec": agent.stat("node_visits") / dt,
+            "nn_evals_per_sec": agent.stat("evals") / dt, "cores": os.cpu_count() or 1, "torch_threads": torch.get_num_threads(),
+            "kind": "port (C search) + torch-CPU fp32 network", "sample": "configs[0] bounded: %d games x breadth %d (%d sims/move), "
+            "depth %d, one root turn, %.1f s" % (games, breadth, (breadth // 8) * 8, depth, dt)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -321,6 +342,11 @@ def run_ours(args, rank, world, local_rank):
     out.update(sp)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
+        if not args.no_selfplay:
+            try:
+                out["mcts_cpu_baseline"] = cpu_selfplay_baseline()
+            except Exception as ex:
+                out["mcts_cpu_baseline"] = {"error": repr(ex)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
