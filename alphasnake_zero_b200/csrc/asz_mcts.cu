@@ -28,6 +28,7 @@
 namespace asz {
 
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+constexpr uint32_t kTouchInvalid = 0xFFFFFFFFu;   // touch stamp of a slot whose insert has not been published yet
 
 struct Table {
   int log2cap = 0;
@@ -90,7 +91,9 @@ __device__ __forceinline__ ProbeResult table_probe(const Table& t, uint64_t k0, 
     if (tag == 0ull) {
       const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(&t.key[h]), 0ull, (unsigned long long)k0);
       if (old == 0ull) {
-        t.chk[h] = k1; t.touch[h] = cur_turn;
+        t.chk[h] = k1;
+        __threadfence();                                                       // publish: check word before the stamp
+        *reinterpret_cast<volatile uint32_t*>(&t.touch[h]) = cur_turn;
         atomicAdd(&stats[ST_INSERTS], 1ull); atomicAdd(&stats[ST_OCCUPIED], 1ull);
         r.slot = (uint32_t)h; r.is_new = true;
         return r;
@@ -98,7 +101,10 @@ __device__ __forceinline__ ProbeResult table_probe(const Table& t, uint64_t k0, 
       tag = old;
     }
     if (tag == k0) {
-      const uint32_t seen = t.touch[h];
+      // a concurrent insert claims the tag first and publishes the stamp last: wait for it (another warp, a few cycles)
+      uint32_t seen;
+      while ((seen = *reinterpret_cast<volatile uint32_t*>(&t.touch[h])) == kTouchInvalid) __nanosleep(32);
+      __threadfence();
       if (seen != cur_turn) {
         if (t.chk[h] != k1) atomicAdd(&stats[ST_COLLISIONS], 1ull);   // same 64-bit tag, different check word
         if (expired(seen, cur_turn, D)) {
@@ -486,6 +492,7 @@ static int table_alloc(Table& t, int log2cap) {
   ASZ_CUDA(cudaMalloc(&t.touch, t.cap * sizeof(uint32_t)));
   ASZ_CUDA(cudaMalloc(&t.eval, t.cap * sizeof(int32_t)));
   ASZ_CUDA(cudaMemset(t.key, 0, t.cap * sizeof(uint64_t)));
+  ASZ_CUDA(cudaMemset(t.touch, 0xFF, t.cap * sizeof(uint32_t)));
   return ASZ_OK;
 }
 static void table_free(Table& t) {
@@ -709,6 +716,7 @@ int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_
   if (occ * 2 > s->tab.cap) {
     if (!s->tab_alt.key) { int rc = table_alloc(s->tab_alt, s->tab.log2cap); if (rc != ASZ_OK) return rc; }
     ASZ_CUDA(cudaMemsetAsync(s->tab_alt.key, 0, s->tab_alt.cap * sizeof(uint64_t), st));
+    ASZ_CUDA(cudaMemsetAsync(s->tab_alt.touch, 0xFF, s->tab_alt.cap * sizeof(uint32_t), st));
     ASZ_CUDA(cudaMemsetAsync(&s->stats[ST_OCCUPIED], 0, sizeof(unsigned long long), st));
     table_rebuild_kernel<<<(unsigned)((s->tab.cap + 255) / 256), 256, 0, st>>>(s->tab, s->tab_alt, s->root_turn, e->cfg.max_depth,
                                                                               &s->stats[ST_OCCUPIED]);
@@ -741,6 +749,7 @@ int asz_search_clear(asz_engine* e, void* stream) {
   SearchState* s = e->search;
   cudaStream_t st = (cudaStream_t)stream;
   ASZ_CUDA(cudaMemsetAsync(s->tab.key, 0, s->tab.cap * sizeof(uint64_t), st));
+  ASZ_CUDA(cudaMemsetAsync(s->tab.touch, 0xFF, s->tab.cap * sizeof(uint32_t), st));
   ASZ_CUDA(cudaMemsetAsync(s->stats, 0, ST_COUNT * sizeof(unsigned long long), st));
   s->root_turn = 0; s->open = false; s->epoch = -1; s->step = 0;
   return ASZ_OK;

@@ -88,7 +88,7 @@ def test_search_replay_against_reference(name):
 
 @pytest.mark.parametrize("side,S,G,D,breadth,base,training,turns", [
     (11, 4, 64, 8, 32, 2.0, True, 6), (7, 4, 32, 4, 16, 100.0, False, 8), (19, 8, 8, 8, 16, 3.0, True, 3),
-    (11, 2, 40, 6, 8, 10.0, True, 12)])
+    (11, 2, 40, 6, 8, 10.0, True, 12), (11, 4, 768, 8, 32, 2.0, True, 2)])
 def test_native_search_against_oracle(side, S, G, D, breadth, base, training, turns):
     """The GPU samples with its own RNG and records the trace; the oracle replays it."""
     import torch
