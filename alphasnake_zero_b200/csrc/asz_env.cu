@@ -75,10 +75,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   using E = EncGeo<G>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
-  // smem: [per-CTA wall pattern][per warp: 2 staging buffers][per warp: board]
+  // smem: [per-CTA wall pattern][per warp: 2 staging buffers][per warp: board][per-CTA body-value table]
   float* s_bg = reinterpret_cast<float*>(smem_raw);
   float* stage0 = s_bg + E::BGLEN + warp * 2 * E::WSTAGE;
   uint16_t* sb = reinterpret_cast<uint16_t*>(s_bg + E::BGLEN + WARPS * 2 * E::WSTAGE) + warp * G::PC;
+  float* s_lut = reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(s_bg + E::BGLEN + WARPS * 2 * E::WSTAGE) + WARPS * G::PC);
+  for (int d = (int)threadIdx.x; d < G::PC + 8; d += WARPS * 32) s_lut[d] = (float)((double)d * 0.02);   // game.py:239, float64 product
   const bool enc = (p.flags & ASZ_STEP_ENCODE) != 0;
   if (enc) {
     fill_wall_pattern(s_bg, E::BGLEN, (int)threadIdx.x, WARPS * 32);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       }
       const int spawn_cell = (p.spawn_mode == ASZ_SPAWN_REPLAY) ? p.spawn_cells[g] : -1;
       const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, p.spawn_mode, spawn_cell, p.chance_thresh, p.seed,
-                                      (uint32_t)g);
+                                      (uint32_t)g, p.S);
       if (p.rewards != nullptr && lane < 8)
         p.rewards[(size_t)g * 8 + lane] = (int8_t)(sn.reward == 1 ? 1 : sn.reward == 2 ? -1 : 0);
       if (lane == 0) {
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         int row = 0;
         if (lane == 0) { row = atomicAdd(p.row_count, n_rows); s_wtot[warp][8] += (uint32_t)n_rows; }
         CellView<G> cv;
-        warp_cell_view<G>(sb, sn, cv);
+        warp_cell_view<G>(sb, sn, cv, s_lut);
         row = __shfl_sync(kFull, row, 0);
         unsigned rest = live_mask;
         while (rest) {
@@ -231,7 +233,8 @@ struct EnvLaunch {
   using G = Geo<SIDE>;
   using E = EncGeo<G>;
   static size_t smem_bytes() {
-    return (size_t)(E::BGLEN + WARPS * 2 * E::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t);
+    return (size_t)(E::BGLEN + WARPS * 2 * E::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t) +
+           (size_t)(G::PC + 8) * sizeof(float);
   }
   template <int MINB>
   static int launch(const EnvParams& p, cudaStream_t st) {

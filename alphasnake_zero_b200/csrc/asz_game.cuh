@@ -106,7 +106,8 @@ __device__ __forceinline__ void warp_init_native(uint16_t* sb, Snake& sn, Meta& 
 // spawn_mode 0: none (sub-games, game.py:268), 1: replay (spawn_cell or -1), 2: native Philox.
 template <class G>
 __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, int move, int health_dec, int spawn_mode,
-                                              int spawn_cell, uint32_t chance_thresh, uint64_t seed, uint32_t game_id) {
+                                              int spawn_cell, uint32_t chance_thresh, uint64_t seed, uint32_t game_id,
+                                              int S = kMaxSnakes) {
   constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS;
   const int lane = lane_id();
   const bool was_alive = sn.alive != 0;
@@ -129,6 +130,7 @@ __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, 
   unsigned blocked = 0;   // head cells among this lane's cells (for the spawn's empty set)
 #pragma unroll
   for (int s2 = 0; s2 < kMaxSnakes; ++s2) {
+    if (s2 >= S) break;                                        // warp-uniform: snake slots >= S are never alive
     const int nh2 = __shfl_sync(kFull, nh, s2);
     const int al2 = __shfl_sync(kFull, (int)was_alive, s2);
     if (al2 && nh2 >= 0) {
@@ -189,6 +191,7 @@ __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, 
   }
 #pragma unroll
   for (int s2 = 0; s2 < kMaxSnakes; ++s2) {
+    if (s2 >= S) break;
     const int nh2 = __shfl_sync(kFull, nh, s2);
     const int al2 = __shfl_sync(kFull, (int)was_alive, s2);
     const int len2 = __shfl_sync(kFull, sn.len, s2);
@@ -237,8 +240,9 @@ struct CellView {
   bool food[G::CPL];
   int8_t cy[G::CPL], cx[G::CPL];   // (y, x) of this lane's cells: constants of the thread
 };
+// body_lut (optional, shared memory): body_lut[d] = float(double(d) * 0.02) for d < G::PC + 8
 template <class G>
-__device__ __forceinline__ void warp_cell_view(const uint16_t* sb, const Snake& sn, CellView<G>& cv) {
+__device__ __forceinline__ void warp_cell_view(const uint16_t* sb, const Snake& sn, CellView<G>& cv, const float* body_lut = nullptr) {
   const int lane = lane_id();
 #pragma unroll
   for (int q = 0; q < G::CPL; ++q) {
@@ -247,7 +251,7 @@ __device__ __forceinline__ void warp_cell_view(const uint16_t* sb, const Snake& 
     const int o = body ? cell_owner(v) : 0;
     const int len_o = __shfl_sync(kFull, sn.len, o);
     const int d = cell_dist(v);
-    cv.f1[q] = body ? (float)((double)d * 0.02) : 0.0f;
+    cv.f1[q] = !body ? 0.0f : (body_lut != nullptr ? body_lut[d] : (float)((double)d * 0.02));
     cv.hs[q] = (int8_t)((body && d == len_o) ? o : -1);
     cv.food[q] = (v == kFood);
     const int c = lane * G::CPL + q;

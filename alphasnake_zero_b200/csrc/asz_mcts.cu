@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32) search_step_kernel(const SearchPar
       }
     }
     // mp_game_runner.py:103-113: tic, then leave when the game ended or the depth is reached
-    const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, ASZ_SPAWN_NONE, -1, 0u, 0ull, 0u);
+    const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, ASZ_SPAWN_NONE, -1, 0u, 0ull, 0u, p.S);
     left = r.ended || (int)m.turn >= p.sub_depth[sub];
     if (lane == 0) atomicAdd(&p.stats[ST_SUBTICS], 1ull);
     // write the record back

@@ -53,14 +53,18 @@ class MPGameRunner:
         return [(int(g), int(s)) for g, s in zip(*np.nonzero(alive))]
 
     # Alice is the agent
-    def run(self, Alice):
+    def run(self, Alice, max_turns=None):
+        """mp_game_runner.py:23-77.  max_turns (extension, default None = the reference's behaviour) stops after that many
+        root turns and leaves the remaining games in self.games so that a later call continues them."""
         t0 = time()
         if self.engine is None:
             self._make_engine(Alice)
         eng, games = self.engine, self.games
-        rewards = [None] * self.game_cnt
         turn = 0
-        while games:
+        if not hasattr(self, "_rewards"):
+            self._rewards = [None] * self.game_cnt
+        rewards = self._rewards
+        while games and (max_turns is None or turn < max_turns):
             turn += 1
             if self.verbose:
                 if len(games) == 1:

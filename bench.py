@@ -101,6 +101,32 @@ def cpu_baseline(target_s=12.0):
                       % (g, tics, st["planes"] / st["steps"], cores, dt)}
 
 
+def selfplay_api_leg(rank, games, breadth, depth, turns):
+    """The same self-play loop through the reference-facing Python API (MPGameRunner.run + Agent.make_moves): host lists of
+    ids and moves, training records copied to the host every root turn (agent.py:93-97)."""
+    import torch
+    from alphasnake_zero_b200.utils.agent import Agent
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    from alphasnake_zero_b200.utils.mp_game_runner import MPGameRunner
+    net = AlphaNNet(input_shape=(2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0, backend="native")
+    alice = Agent(net, 2, True, depth, breadth)
+    gr = MPGameRunner(SIDE, SIDE, SNAKES, HEALTH_DEC, games, seed=5 + rank, verbose=False)
+    gr.run(alice, max_turns=1)                       # warm-up root turn (builds the engine)
+    torch.cuda.synchronize()
+    s0 = gr.engine.search_stats()
+    n0 = len(alice.records)
+    t0 = time.time()
+    gr.run(alice, max_turns=turns)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    s1 = gr.engine.search_stats()
+    rec_bytes = (len(alice.records) - n0) * (PLANE_BYTES + 12)
+    return {"sims_per_sec": (s1["subgames"] - s0["subgames"]) / dt, "nn_evals_per_sec": (s1["evals"] - s0["evals"]) / dt,
+            "root_turns": turns, "seconds": dt, "records": len(alice.records) - n0,
+            "d2h_bytes_per_turn": rec_bytes / max(turns, 1) + games * 8 * 13, "h2d_bytes_per_turn": games * 8,
+            "api": "MPGameRunner(%d games).run(Agent(net, 2, True, %d, %d), max_turns=%d)" % (games, depth, breadth, turns)}
+
+
 def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True):
     """configs[2] of BASELINE.json (scaled by --sp-games): self-play root turns with the search kernels and the
     hand-written value network.  A simulation = one sub-game rollout (agent.py:37-56)."""
@@ -295,6 +321,11 @@ def run_ours(args, rank, world, local_rank):
                 sp[key] = r
             except Exception as ex:   # the headline line must still be printed
                 sp[key] = {"error": repr(ex)}
+        if world == 1:
+            try:
+                sp["mcts_e2e"] = selfplay_api_leg(rank, args.sp_games, 100, 8, args.sp_turns)
+            except Exception as ex:
+                sp["mcts_e2e"] = {"error": repr(ex)}
 
     # ---- reduce over ranks: max time, sum of work ----------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local)], dtype=torch.float64, device=dev)
