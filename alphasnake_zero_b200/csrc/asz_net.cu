@@ -100,6 +100,53 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- CTA-pair (cta_group::2) wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope) on purpose: a cluster-scope
+// release compiles to MEMBAR.ALL.GPU, and what these arrivals order (bulk-copy bytes seen through complete_tx, TMEM reads
+// fenced by tcgen05.fence::before_thread_sync) does not travel through the generic proxy.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// one MMA over the CTA pair: M = 256 (128 rows of A and of D in each CTA), B split along N between the two CTAs
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in both CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // shared-memory matrix descriptor, K-major, no swizzle: 8x(16 B) core matrices, LBO = byte distance between the two
 // 16-byte K chunks of one K=16 step, SBO = byte distance between 8-row groups (cute/arch/mma_sm100_desc.hpp layout:
 // start [0,14), LBO [16,30), SBO [32,46), version [46,48) = 1, layout type [61,64) = 0)
@@ -110,6 +157,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor kind::f16: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9, 10-12 = 1), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)((2 * kTileM) >> 4) << 24);
 
 // ---- convolution kernel -----------------------------------------------------------------------------------------
 struct ConvParams {
@@ -264,33 +312,69 @@ __global__ void __launch_bounds__(192, 1) conv_tile_kernel(const ConvParams p) {
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, kC); }
 }
 
-// ---- persistent convolution kernel (v2) -----------------------------------------------------------------------------
-// One CTA per SM loops over super-tiles of 256 positions.  Per super-tile the weights stream through shared memory
-// once (half a tap = 16 KB per stage) and feed two M=128 accumulators, so the L2 -> SM weight traffic per output row is
-// half of conv_tile_kernel's; TMEM holds two accumulator pairs (4 x 128 columns) so that the epilogue of super-tile i
-// overlaps the MMAs of super-tile i+1, and the activation halo tile is double buffered the same way.
+// ---- persistent convolution kernel (single CTA or CTA pair) -------------------------------------------------------------
+// One CTA per SM loops over super-tiles of 256 positions.  Per super-tile the weights stream through shared memory once
+// (half a tap per stage) and feed two M=128 accumulators; TMEM holds two accumulator pairs (4 x 128 columns) so that the
+// epilogue of super-tile i overlaps the MMAs of super-tile i+1.
 //   warp 0      producer  : cp.async.bulk of the A halo tile and of the weight chunks, mbarrier complete_tx
-//   warp 1      MMA issuer: one thread, tcgen05.mma M128 N128 K16, tcgen05.commit releases stages / publishes accumulators
-//   warps 2..5  epilogue  : tcgen05.ld, BN scale/bias, residual, ReLU, padding mask, bf16 store (or the fused head conv)
-template <int HALO>
-struct PersistSmem {
-  static constexpr int kSuper = 256;
+//   warp 1      MMA issuer: one elected thread, tcgen05.mma M128 N128 K16, tcgen05.commit releases stages / publishes accumulators
+//   warps 2..9  epilogue  : tcgen05.ld, BN scale/bias, residual, ReLU, padding mask, bf16 store (or the fused head conv)
+// Loop order inside a super-tile: channel half c (8 of the 16 chunks) outermost, then the 9 taps.  The A half c is
+// released as soon as its 9 taps are issued, so the next super-tile's half 0 streams in while half 1 is being consumed:
+// the halo tile is effectively double buffered at 1x its size, which leaves room for 9+ weight stages.
+//
+// The MMA issue loop is written for issue rate: an M128 N128 K16 MMA lasts 64 tensor cycles, and ONE thread has to issue
+// them back to back.  (tools/umma_probe.cu: the tensor pipe sustains 64.1 clk per MMA for every operand layout and shape
+// tried, with bulk-copy fills running; the first version of this loop spent 196 SASS instructions per 8 MMAs rebuilding
+// descriptors and walking divergence waterfalls and reached 46 % of that.)  So: the whole warp runs the loop in uniform
+// control flow, one elected lane issues; loops have compile-time trip counts; a descriptor's low word is base + constant.
+//
+// PAIR = true: the two CTAs of a cluster (the two SMs of a TPC) issue ONE tcgen05.mma.cta_group::2 of M = 256: every CTA
+// supplies its own 128 rows of A (its own halo tile) but only HALF of the weights (64 of the 128 output channels).
+//   work unit   a pair super-tile of 512 positions: CTA r owns positions [512 st + 256 r, +256)
+//   rank 0      issues the MMAs of the pair; rank 1's warp 1 relays "my operands have landed" to rank 0's full barriers
+//   barriers    full barriers of rank 0 count 2 arrivals (own producer + the relay); empty / accumulator-full barriers are
+//               signalled in both CTAs by a multicast tcgen05.commit; accumulator-empty lives in rank 0 and counts the 16
+//               epilogue warps of the pair.
+//   weights     pair layout [tap][half][rank][8 kc][64 cout][8] (pair_weight_layout_kernel): a chunk is one bulk copy and
+//               is fetched from L2 once per CTA pair.
+template <int HALO, bool PAIR>
+struct UmmaSmem {
+  static constexpr int kSuper = 256;                               // positions per CTA and weight pass
   static constexpr int rows = kSuper + 2 * HALO;
-  static constexpr size_t a_bytes = (size_t)kKC * rows * 16;      // one halo tile, managed as two channel halves
-  static constexpr size_t b_chunk = (size_t)8 * kC * 16;          // half a tap = 16 KB
-  static constexpr size_t tail = 3 * kC * sizeof(float) + 40 * sizeof(uint64_t) + 64;
-  static constexpr int b_stages = (int)((232448 - a_bytes - tail) / b_chunk);   // 9 at HALO 24, 8 at HALO 40
+  static constexpr size_t a_bytes = (size_t)kKC * rows * 16;       // one halo tile, managed as two channel halves
+  static constexpr int b_rows = PAIR ? kC / 2 : kC;                // output channels whose weights this CTA holds
+  static constexpr size_t b_chunk = (size_t)8 * b_rows * 16;       // half a tap: 16 KB (8 KB per CTA of a pair)
+  static constexpr int max_stages = 16;
+  static constexpr size_t tail = 3 * kC * sizeof(float) + (8 + 2 * max_stages) * sizeof(uint64_t) + 64;
+  static constexpr int raw_stages = (int)((232448 - a_bytes - tail) / b_chunk);
+  static constexpr int b_stages = raw_stages > max_stages ? max_stages : raw_stages;   // 9 / 8 single, 16 pair
   static constexpr size_t total = a_bytes + b_stages * b_chunk + tail;
 };
 
-// Loop order inside a super-tile: channel half c (8 of the 16 chunks) outermost, then the 9 taps.  The A half c is
-// released as soon as its 9 taps are issued, so the next super-tile's half 0 streams in while half 1 is being consumed
-// (and vice versa): the halo tile is effectively double buffered at 1x its size, which leaves room for 8-9 weight
-// stages -- enough chunks in flight to cover the L2 latency of the weight stream.
-template <int HALO>
-__global__ void __launch_bounds__(320, 1) conv_persist_kernel(const ConvParams p, int n_super) {
-  using SM = PersistSmem<HALO>;
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xFFFFFFFF;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
+// FIRST = the first convolution (one tap over K = 32 im2col rows, 4 channel chunks); otherwise 9 taps x 16 chunks
+template <int HALO, bool PAIR, bool FIRST>
+__global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, int n_tiles) {
+  using SM = UmmaSmem<HALO, PAIR>;
   constexpr int NS = SM::b_stages;
+  constexpr int KC_HALF = FIRST ? 4 : 8;
+  constexpr int HALVES = FIRST ? 1 : 2;
+  constexpr int TAPS = FIRST ? 1 : 9;
+  constexpr int TILE = PAIR ? 2 * SM::kSuper : SM::kSuper;         // positions per work unit
+  constexpr uint32_t chunk_bytes = (uint32_t)(KC_HALF * SM::b_rows * 16);
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
   unsigned char* sB = smem + SM::a_bytes;
@@ -301,96 +385,140 @@ __global__ void __launch_bounds__(320, 1) conv_persist_kernel(const ConvParams p
   uint64_t* a_full = bars;             // [2] channel halves
   uint64_t* a_empty = bars + 2;        // [2]
   uint64_t* acc_full = bars + 4;       // [2] accumulator pairs
-  uint64_t* acc_empty = bars + 6;      // [2]
+  uint64_t* acc_empty = bars + 6;      // [2] (of rank 0 in a pair)
   uint64_t* b_full = bars + 8;         // [NS]
-  uint64_t* b_empty = bars + 8 + NS;   // [NS]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NS);
-  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
-  const int kc_in = p.kc_in, taps = p.taps;
-  const int kc_half = kc_in < 8 ? kc_in : 8;
-  const int halves = kc_in / kc_half;
-  const uint32_t chunk_bytes = (uint32_t)(kc_half * kC * 16);
+  uint64_t* b_empty = bars + 8 + SM::max_stages;   // [NS]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8 + 2 * SM::max_stages);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = (int)(threadIdx.x & 31);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   for (int i = (int)threadIdx.x; i < kC; i += (int)blockDim.x) {
     s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i];
     s_head[i] = p.head_w ? p.head_w[i] : 0.0f;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
-    for (int i = 0; i < NS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    const uint32_t full_count = (PAIR && rank == 0) ? 2u : 1u;
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 16 : 8);
+    }
+    for (int i = 0; i < NS; ++i) { mbar_init(&b_full[i], full_count); mbar_init(&b_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(s_tmem, 512);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(s_tmem, 512); else tmem_alloc(s_tmem, 512); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t bit = 0, it = 0;
-      for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
-        const size_t row0 = (size_t)kGuard + (size_t)st * SM::kSuper - HALO;
-        for (int c = 0; c < halves; ++c) {
+      // ---- producer ----
+      uint32_t stage = 0, phase = 0, it = 0;
+      const __nv_bfloat16* wt = p.wt + (PAIR ? (size_t)rank * (chunk_bytes / 2) : 0);
+      constexpr size_t chunk_stride = (size_t)(PAIR ? 2 : 1) * (chunk_bytes / 2);        // bf16 elements between chunks
+      for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
+        const size_t row0 = (size_t)kGuard + (size_t)st * TILE + (size_t)rank * SM::kSuper - HALO;
+#pragma unroll 1
+        for (int c = 0; c < HALVES; ++c) {
           mbar_wait(&a_empty[c], (it & 1u) ^ 1u);
-          mbar_expect_tx(&a_full[c], (uint32_t)(kc_half * SM::rows * 16));
-          for (int k = 0; k < kc_half; ++k) {
-            const int kc = c * kc_half + k;
+          mbar_expect_tx(&a_full[c], (uint32_t)(KC_HALF * SM::rows * 16));
+#pragma unroll
+          for (int k = 0; k < KC_HALF; ++k) {
+            const int kc = c * KC_HALF + k;
             bulk_g2s(sA + (size_t)kc * SM::rows * 16, p.in + ((size_t)kc * p.P_tot + row0) * 8, SM::rows * 16, &a_full[c]);
           }
-          for (int t = 0; t < taps; ++t, ++bit) {
-            const int s = (int)(bit % NS);
-            mbar_wait(&b_empty[s], ((bit / NS) & 1u) ^ 1u);
-            mbar_expect_tx(&b_full[s], chunk_bytes);
-            bulk_g2s(sB + (size_t)s * SM::b_chunk, p.wt + ((size_t)t * kc_in + (size_t)c * kc_half) * kC * 8, chunk_bytes, &b_full[s]);
+#pragma unroll 1
+          for (int t = 0; t < TAPS; ++t) {
+            mbar_wait(&b_empty[stage], phase ^ 1u);
+            mbar_expect_tx(&b_full[stage], chunk_bytes);
+            // single layout [tap][kc][128][8]: chunk (t, c) starts at (t * HALVES + c) * KC_HALF * 128 * 8
+            // pair layout   [tap][half][rank][KC_HALF][64][8]: chunk (t, c, rank) = ((t * HALVES + c) * 2 + rank) * chunk
+            bulk_g2s(sB + (size_t)stage * SM::b_chunk, wt + (size_t)(t * HALVES + c) * chunk_stride, chunk_bytes, &b_full[stage]);
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t bit = 0, it = 0;
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
-        const int buf = (int)(it & 1u);
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator pair
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
-        uint32_t first = 1;
-        for (int c = 0; c < halves; ++c) {
+    if (!PAIR || rank == 0) {
+      // ---- MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues ----
+      const bool issuer = elect_one();
+      const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | ((uint32_t)SM::rows << 16);      // LBO = rows * 16 B
+      const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFFu) | ((uint32_t)SM::b_rows << 16);    // LBO = b_rows * 16 B
+      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);                                     // SBO = 128 B, version 1
+      constexpr uint32_t idesc = PAIR ? kIdescPair : kIdesc;
+      const int pitch = p.pitch;
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // the epilogue(s) have drained this accumulator pair
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * 256u;
+#pragma unroll 1
+        for (int c = 0; c < HALVES; ++c) {
           mbar_wait(&a_full[c], it & 1u);
           tc_fence_after();
-          for (int t = 0; t < taps; ++t, ++bit) {
-            const int shift = (taps == 1) ? 0 : ((t / 3) - 1) * p.pitch + ((t % 3) - 1);
-            const int s = (int)(bit % NS);
-            mbar_wait(&b_full[s], (bit / NS) & 1u);
-            tc_fence_after();
+          const uint32_t a_c = a_lo0 + (uint32_t)(c * KC_HALF * SM::rows + HALO);
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              for (int ks = 0; ks < kc_half / 2; ++ks) {
-                const int kc = c * kc_half + 2 * ks;
-                const uint32_t a_addr = a_base + (uint32_t)((kc * SM::rows + HALO + shift + sub * kTileM) * 16);
-                const uint32_t b_addr = b_base + (uint32_t)(s * SM::b_chunk) + (uint32_t)((2 * ks) * kC * 16);
-                umma_bf16(tmem_d + (uint32_t)(sub * kC), smem_desc(a_addr, SM::rows * 16, 128), smem_desc(b_addr, kC * 16, 128), kIdesc,
-                          (first && ks == 0) ? 0u : 1u);
+          for (int t = 0; t < TAPS; ++t) {
+            const int shift = (TAPS == 1) ? 0 : ((t / 3) - 1) * pitch + ((t % 3) - 1);
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            if (issuer) {
+              const uint32_t a_t = a_c + (uint32_t)shift;
+              const uint32_t b_s = b_lo0 + stage * (uint32_t)(SM::b_chunk >> 4);
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                for (int ks = 0; ks < KC_HALF / 2; ++ks) {
+                  const uint64_t ad = desc64(a_t + (uint32_t)(sub * kTileM + 2 * ks * SM::rows), desc_hi);
+                  const uint64_t bd = desc64(b_s + (uint32_t)(2 * ks * SM::b_rows), desc_hi);
+                  const uint32_t acc = (t == 0 && ks == 0) ? (uint32_t)c : 1u;
+                  if (PAIR) umma_bf16_pair(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
+                  else umma_bf16(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
+                }
               }
+              if (PAIR) umma_commit_pair(&b_empty[stage]); else umma_commit(&b_empty[stage]);
             }
-            first = 0;
-            umma_commit(&b_empty[s]);
+            __syncwarp();
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&a_empty[c]);      // this channel half of the halo tile may be overwritten by the next super-tile
+          if (issuer) { if (PAIR) umma_commit_pair(&a_empty[c]); else umma_commit(&a_empty[c]); }
         }
-        umma_commit(&acc_full[buf]);
+        if (issuer) { if (PAIR) umma_commit_pair(&acc_full[buf]); else umma_commit(&acc_full[buf]); }
+        __syncwarp();
+      }
+    } else if (lane == 0) {
+      // ---- relay of rank 1: tell rank 0's full barriers that this CTA's operands have landed ----
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
+#pragma unroll 1
+        for (int c = 0; c < HALVES; ++c) {
+          mbar_wait(&a_full[c], it & 1u);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[c]), 0));
+#pragma unroll 1
+          for (int t = 0; t < TAPS; ++t) {
+            mbar_wait(&b_full[stage], phase);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&b_full[stage]), 0));
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+          }
+        }
       }
     }
   } else {
-    // 8 epilogue warps: warps 2..5 take rows 0..127 of the super-tile (sub 0), warps 6..9 rows 128..255 (sub 1);
+    // 8 epilogue warps: warps 2..5 take rows 0..127 of this CTA's super-tile (sub 0), warps 6..9 rows 128..255 (sub 1);
     // a warp may only touch the TMEM lane quarter warp % 4.  One thread = one output row (position), 128 channels.
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
     uint32_t it = 0;
-    for (int st = (int)blockIdx.x; st < n_super; st += (int)gridDim.x, ++it) {
+    for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
       const int buf = (int)(it & 1u);
-      const int pos = st * SM::kSuper + sub * kTileM + q * 32 + lane;
+      const int pos = st * TILE + (int)rank * SM::kSuper + sub * kTileM + q * 32 + lane;
       const int rem = pos % p.img_stride;
       const int y = rem / p.pitch, x = rem - y * p.pitch;
       const bool valid = pos < p.P_real && y < p.real && x < p.real;
@@ -437,11 +565,31 @@ __global__ void __launch_bounds__(320, 1) conv_persist_kernel(const ConvParams p
       if (p.head_out != nullptr) p.head_out[grow] = valid ? fmaxf(head_acc * p.head_scale + p.head_bias, 0.0f) : 0.0f;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+        else mbar_arrive(&acc_empty[buf]);
+      }
     }
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (PAIR) cluster_sync_all();   // nobody leaves (or frees tensor memory) while the peer can still signal or accumulate
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// [tap][kc][128 cout][8] -> [tap][half][rank][kc % 8][64 cout][8]: each (tap, half, rank) chunk is one contiguous bulk copy
+__global__ void pair_weight_layout_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int taps, int kc_in) {
+  const int kc_half = kc_in < 8 ? kc_in : 8, halves = kc_in / kc_half;
+  const int total = taps * kc_in * kC;                       // 16-byte elements
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= total) return;
+  const int cout = i % kC, kc = (i / kC) % kc_in, t = i / (kC * kc_in);
+  const int c = kc / kc_half, k = kc % kc_half, r = cout / (kC / 2), co = cout % (kC / 2);
+  const size_t o = ((((size_t)t * halves + c) * 2 + r) * kc_half + k) * (kC / 2) + co;
+  reinterpret_cast<uint4*>(dst)[o] = reinterpret_cast<const uint4*>(src)[i];
 }
 
 // ---- input preparation: fp32 NHWC planes -> bf16 im2col rows of the first convolution (K = 27 padded to 32) --------
@@ -501,6 +649,42 @@ __global__ void __launch_bounds__(128) dense_head_kernel(const float* __restrict
   }
 }
 
+template <int HALO, bool PAIR, bool FIRST>
+static int configure_one() {
+  return cuda_ok(cudaFuncSetAttribute(conv_umma_kernel<HALO, PAIR, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)UmmaSmem<HALO, PAIR>::total), "cudaFuncSetAttribute(conv_umma_kernel)") ? ASZ_OK : ASZ_ERR_CUDA;
+}
+static int configure_umma_kernels() {
+  int rc = ASZ_OK;
+  if ((rc = configure_one<24, false, false>()) != ASZ_OK) return rc;
+  if ((rc = configure_one<24, false, true>()) != ASZ_OK) return rc;
+  if ((rc = configure_one<40, false, false>()) != ASZ_OK) return rc;
+  if ((rc = configure_one<40, false, true>()) != ASZ_OK) return rc;
+  if ((rc = configure_one<24, true, false>()) != ASZ_OK) return rc;
+  if ((rc = configure_one<24, true, true>()) != ASZ_OK) return rc;
+  if ((rc = configure_one<40, true, false>()) != ASZ_OK) return rc;
+  if ((rc = configure_one<40, true, true>()) != ASZ_OK) return rc;
+  return rc;
+}
+template <int HALO, bool PAIR, bool FIRST>
+static int launch_one(int grid, const ConvParams& p, int n_tiles, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = UmmaSmem<HALO, PAIR>::total; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cuda_ok(cudaLaunchKernelEx(&cfg, conv_umma_kernel<HALO, PAIR, FIRST>, p, n_tiles), "conv_umma_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
+}
+static int launch_umma(bool pair, bool big, bool first, int grid, const ConvParams& p, int n_tiles, cudaStream_t st) {
+  if (!big) {
+    if (!pair) return first ? launch_one<24, false, true>(grid, p, n_tiles, st) : launch_one<24, false, false>(grid, p, n_tiles, st);
+    return first ? launch_one<24, true, true>(grid, p, n_tiles, st) : launch_one<24, true, false>(grid, p, n_tiles, st);
+  }
+  if (!pair) return first ? launch_one<40, false, true>(grid, p, n_tiles, st) : launch_one<40, false, false>(grid, p, n_tiles, st);
+  return first ? launch_one<40, true, true>(grid, p, n_tiles, st) : launch_one<40, true, false>(grid, p, n_tiles, st);
+}
+
 }  // namespace asz
 
 using namespace asz;
@@ -514,7 +698,9 @@ struct asz_net {
   __nv_bfloat16* col = nullptr;   // im2col input of the first layer [4][P_tot][8]
   float* head = nullptr;          // [P_tot]
   int n_sm = 148;
-  int variant = 2;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_persist_kernel)
+  int variant = 2;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_umma_kernel, one CTA per SM),
+                                  // 3 = persistent over CTA pairs (conv_umma_kernel PAIR, cta_group::2)
+  __nv_bfloat16* w_pair[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st);
@@ -531,7 +717,7 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
   if (n->pitch + 1 > kHalo) { set_error("board too large for the halo of conv_tile_kernel"); delete n; return ASZ_ERR_ARG; }
   n->chunk = chunk_images;
   const size_t P = (size_t)chunk_images * n->img_stride;
-  const size_t P_pad = (P + 255) / 256 * 256;
+  const size_t P_pad = (P + 511) / 512 * 512;                 // whole pair super-tiles
   n->P_tot = (int)(kGuard + P_pad + kGuard + kHalo);
   const size_t act_bytes = (size_t)kKC * n->P_tot * 8 * sizeof(__nv_bfloat16);
   for (int i = 0; i < 3; ++i) {
@@ -543,16 +729,23 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
   ASZ_CUDA(cudaMalloc(&n->head, (size_t)n->P_tot * sizeof(float)));
   ASZ_CUDA(cudaMemset(n->head, 0, (size_t)n->P_tot * sizeof(float)));
   ASZ_CUDA(cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvSmem::total));
-  ASZ_CUDA(cudaFuncSetAttribute(conv_persist_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistSmem<24>::total));
-  ASZ_CUDA(cudaFuncSetAttribute(conv_persist_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistSmem<40>::total));
   {
     int dev = 0; cudaDeviceProp prop;
     ASZ_CUDA(cudaGetDevice(&dev));
     ASZ_CUDA(cudaGetDeviceProperties(&prop, dev));
     n->n_sm = prop.multiProcessorCount;
     const char* v = getenv("ASZ_NET_VARIANT");
-    if (v && v[0] == '1') n->variant = 1;
+    if (v && v[0] >= '1' && v[0] <= '3') n->variant = v[0] - '0';
   }
+  { int rc = configure_umma_kernels(); if (rc != ASZ_OK) { delete n; return rc; } }
+  for (int l = 0; l < 9; ++l) {
+    const int taps = l == 0 ? 1 : 9, kc_in = l == 0 ? 4 : kKC;
+    const int total = taps * kc_in * kC;
+    ASZ_CUDA(cudaMalloc(&n->w_pair[l], (size_t)total * 16));
+    pair_weight_layout_kernel<<<(total + 255) / 256, 256>>>(reinterpret_cast<const __nv_bfloat16*>(w->w_conv[l]), n->w_pair[l], taps, kc_in);
+    ASZ_CUDA(cudaGetLastError());
+  }
+  ASZ_CUDA(cudaDeviceSynchronize());
   *out = n;
   return ASZ_OK;
 }
@@ -561,6 +754,7 @@ int asz_net_destroy(asz_net* n) {
   if (!n) return ASZ_OK;
   for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
   cudaFree(n->col); cudaFree(n->head);
+  for (int l = 0; l < 9; ++l) cudaFree(n->w_pair[l]);
   delete n;
   return ASZ_OK;
 }
@@ -581,11 +775,19 @@ static int launch_conv(asz_net* n, int layer, const __nv_bfloat16* in, const __n
     conv_tile_kernel<<<tiles, 192, ConvSmem::total, st>>>(p);
     return cuda_ok(cudaGetLastError(), "conv_tile_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
   }
-  const int n_super = (p.P_real + 255) / 256;
-  const int grid = std::min(n_super, n->n_sm);
-  if (n->pitch + 1 <= 24) conv_persist_kernel<24><<<grid, 320, PersistSmem<24>::total, st>>>(p, n_super);
-  else conv_persist_kernel<40><<<grid, 320, PersistSmem<40>::total, st>>>(p, n_super);
-  return cuda_ok(cudaGetLastError(), "conv_persist_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
+  const bool pair = n->variant == 3;
+  if (pair) p.wt = n->w_pair[layer];
+  const bool big = n->pitch + 1 > 24;
+  const int n_tiles = pair ? (p.P_real + 511) / 512 : (p.P_real + 255) / 256;
+  const int grid = pair ? 2 * std::min(n_tiles, n->n_sm / 2) : std::min(n_tiles, n->n_sm);
+  return launch_umma(pair, big, layer == 0, grid, p, n_tiles, st);
+}
+
+int asz_net_set_variant(asz_net* n, int32_t variant) {
+  if (!n) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if (variant < 1 || variant > 3) { set_error("variant must be 1 (tile), 2 (persistent) or 3 (CTA pair)"); return ASZ_ERR_ARG; }
+  n->variant = variant;
+  return ASZ_OK;
 }
 
 int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_values, void* stream) {

@@ -34,7 +34,7 @@ def _conv0_layout(k):
 
 class NativeNet:
 
-    def __init__(self, weights, device, chunk_images=4096):
+    def __init__(self, weights, device, chunk_images=4096, variant=None):
         if not torch.cuda.is_available():
             raise _lib.AszError("no CUDA device: the native network has no CPU fallback")
         self.device = torch.device(device)
@@ -71,6 +71,8 @@ class NativeNet:
         with torch.cuda.device(dev):
             check(self.L.asz_net_create(C.byref(h), C.byref(nw), chunk_images))
         self.h = h
+        if variant is not None:
+            check(self.L.asz_net_set_variant(self.h, int(variant)))
 
     def __del__(self):
         try:

@@ -14,14 +14,14 @@ FLOPS = {7: None, 11: 1043724288, 19: 3240040448}
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-    side = int(sys.argv[2]) if len(sys.argv) > 2 else 11
-    chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n = int(argv[0]) if len(argv) > 0 else 16384
+    side = int(argv[1]) if len(argv) > 1 else 11
+    chunk = int(argv[2]) if len(argv) > 2 else 4096
     N = 2 * side - 1
     w = init_weights((N, N, 3), seed=0)
     x = torch.rand(n, N, N, 3, device="cuda") * 0.5
     out = {}
-    nat = NativeNet(w, "cuda", chunk_images=chunk)
     tnet = AlphaNNet(weights=w, backend="torch")
 
     def timeit(fn, reps=5):
@@ -35,8 +35,14 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
-    t = timeit(lambda: nat.forward(x))
-    out["native_bf16"] = {"evals_per_s": n / t, "tflops": n / t * FLOPS[side] / 1e12 if FLOPS[side] else None, "ms": t * 1e3}
+    for v in (2, 3):
+        nat = NativeNet(w, "cuda", chunk_images=chunk, variant=v)
+        t = timeit(lambda: nat.forward(x))
+        out["native_bf16_v%d" % v] = {"evals_per_s": n / t, "tflops": n / t * FLOPS[side] / 1e12 if FLOPS[side] else None, "ms": t * 1e3}
+        del nat
+    if "--no-torch" in sys.argv:
+        print(json.dumps({"n": n, "side": side, "chunk": chunk, **out}))
+        return
     with torch.no_grad():
         for name, dt in (("torch_bf16", torch.bfloat16), ("torch_fp32", torch.float32)):
             bs = 4096
