@@ -698,7 +698,7 @@ struct asz_net {
   __nv_bfloat16* col = nullptr;   // im2col input of the first layer [4][P_tot][8]
   float* head = nullptr;          // [P_tot]
   int n_sm = 148;
-  int variant = 2;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_umma_kernel, one CTA per SM),
+  int variant = 3;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_umma_kernel, one CTA per SM),
                                   // 3 = persistent over CTA pairs (conv_umma_kernel PAIR, cta_group::2)
   __nv_bfloat16* w_pair[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };

@@ -391,7 +391,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play (MCTS + value net) leg")
-    ap.add_argument("--sp-games", type=int, default=1024, help="root games of the self-play leg (configs[2] uses 4096)")
+    ap.add_argument("--sp-games", type=int, default=4096, help="root games of the self-play leg (configs[2]: 4096)")
     ap.add_argument("--sp-turns", type=int, default=2, help="timed root turns of the self-play leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
