@@ -626,28 +626,45 @@ __global__ void im2col_kernel(const float* __restrict__ planes, int n_img, int r
   }
 }
 
-// ---- dense head: Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54), one CTA per image ------------
-__global__ void __launch_bounds__(128) dense_head_kernel(const float* __restrict__ head /* [P_tot] */, int real, int pitch, int img_stride,
-                                                         const float* __restrict__ w1 /* [real*real][128] */, const float* __restrict__ b1,
-                                                         const float* __restrict__ w2 /* [128][3] */, const float* __restrict__ b2,
-                                                         float* __restrict__ out /* [n][3] */) {
-  extern __shared__ float sh[];          // real*real + 128
+// ---- dense head: Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54), IMG images per CTA ----------------
+// thread t owns hidden unit t for all IMG images, so one pass over the 226 KB (11x11) of dense1 weights serves IMG images
+template <int IMG>
+__global__ void __launch_bounds__(128) dense_head_kernel(const float* __restrict__ head /* [P_tot] */, int n_img, int real, int pitch,
+                                                         int img_stride, const float* __restrict__ w1 /* [real*real][128] */,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2 /* [128][3] */,
+                                                         const float* __restrict__ b2, float* __restrict__ out /* [n][3] */) {
+  extern __shared__ float sh[];          // [IMG][real*real] inputs, then [IMG][128] hidden
+  const int rr = real * real;
   float* s_in = sh;
-  float* s_h = sh + real * real;
-  const int n = (int)blockIdx.x, tid = (int)threadIdx.x;
-  const float* src = head + kGuard + (size_t)n * img_stride;
-  for (int i = tid; i < real * real; i += 128) { const int y = i / real, x = i - y * real; s_in[i] = src[y * pitch + x]; }
+  float* s_h = sh + IMG * rr;
+  const int n0 = (int)blockIdx.x * IMG, tid = (int)threadIdx.x;
+  for (int i = tid; i < IMG * rr; i += 128) {
+    const int j = i / rr, r = i - j * rr;
+    const int y = r / real, x = r - y * real;
+    s_in[i] = (n0 + j < n_img) ? head[kGuard + (size_t)(n0 + j) * img_stride + y * pitch + x] : 0.0f;
+  }
   __syncthreads();
-  float acc = b1[tid];
-  for (int i = 0; i < real * real; ++i) acc = fmaf(s_in[i], w1[(size_t)i * 128 + tid], acc);
-  s_h[tid] = fmaxf(acc, 0.0f);
+  float acc[IMG];
+#pragma unroll
+  for (int j = 0; j < IMG; ++j) acc[j] = b1[tid];
+  for (int i = 0; i < rr; ++i) {
+    const float w = w1[(size_t)i * 128 + tid];
+#pragma unroll
+    for (int j = 0; j < IMG; ++j) acc[j] = fmaf(s_in[j * rr + i], w, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < IMG; ++j) s_h[j * 128 + tid] = fmaxf(acc[j], 0.0f);
   __syncthreads();
-  if (tid < 3) {
-    float o = b2[tid];
-    for (int j = 0; j < 128; ++j) o = fmaf(s_h[j], w2[j * 3 + tid], o);
-    out[(size_t)n * 3 + tid] = tanhf(o);
+  if (tid < IMG * 3) {
+    const int j = tid / 3, k = tid - j * 3;
+    if (n0 + j < n_img) {
+      float o = b2[k];
+      for (int u = 0; u < 128; ++u) o = fmaf(s_h[j * 128 + u], w2[u * 3 + k], o);
+      out[(size_t)(n0 + j) * 3 + k] = tanhf(o);
+    }
   }
 }
+
 
 template <int HALO, bool PAIR, bool FIRST>
 static int configure_one() {
@@ -738,6 +755,7 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
     if (v && v[0] >= '1' && v[0] <= '3') n->variant = v[0] - '0';
   }
   { int rc = configure_umma_kernels(); if (rc != ASZ_OK) { delete n; return rc; } }
+  ASZ_CUDA(cudaFuncSetAttribute(dense_head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   for (int l = 0; l < 9; ++l) {
     const int taps = l == 0 ? 1 : 9, kc_in = l == 0 ? 4 : kKC;
     const int total = taps * kc_in * kC;
@@ -828,8 +846,11 @@ static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, fl
     export_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(act, head, m, n->real, n->pitch, n->img_stride, n->P_tot, d_act);
     return cuda_ok(cudaGetLastError(), "export_act_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
   };
-  for (int i0 = 0; i0 < count; i0 += n->chunk) {
-    const int m = std::min(n->chunk, count - i0);
+  // balanced passes: ceil(count / chunk) passes of (almost) equal size, so that no pass is a sliver that leaves SMs idle
+  const int n_pass = (count + n->chunk - 1) / n->chunk;
+  const int per_pass = n_pass > 0 ? (count + n_pass - 1) / n_pass : 0;
+  for (int i0 = 0; i0 < count; i0 += per_pass) {
+    const int m = std::min(per_pass, count - i0);
     const int P = m * n->img_stride;
     im2col_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_planes + (size_t)i0 * plane, m, n->real, n->pitch, n->img_stride, n->P_tot, n->col);
     if (!cuda_ok(cudaGetLastError(), "im2col_kernel")) return ASZ_ERR_CUDA;
@@ -848,8 +869,12 @@ static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, fl
       if (stop_layer == 2 + 2 * b) return last ? dump(nullptr, n->head, m) : dump(n->act[y], nullptr, m);
       x = y;
     }
-    dense_head_kernel<<<m, 128, (size_t)(n->real * n->real + 128) * sizeof(float), st>>>(
-        n->head, n->real, n->pitch, n->img_stride, n->w.dense1_w, n->w.dense1_b, n->w.dense2_w, n->w.dense2_b, d_values + (size_t)i0 * 3);
+    {
+      constexpr int IMG = 8;
+      const size_t sh = (size_t)IMG * (n->real * n->real + 128) * sizeof(float);
+      dense_head_kernel<IMG><<<(m + IMG - 1) / IMG, 128, sh, st>>>(n->head, m, n->real, n->pitch, n->img_stride, n->w.dense1_w, n->w.dense1_b,
+                                                                  n->w.dense2_w, n->w.dense2_b, d_values + (size_t)i0 * 3);
+    }
     if (!cuda_ok(cudaGetLastError(), "dense_head_kernel")) return ASZ_ERR_CUDA;
   }
   return ASZ_OK;

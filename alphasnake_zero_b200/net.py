@@ -34,7 +34,7 @@ def _conv0_layout(k):
 
 class NativeNet:
 
-    def __init__(self, weights, device, chunk_images=4096, variant=None):
+    def __init__(self, weights, device, chunk_images=16384, variant=None):
         if not torch.cuda.is_available():
             raise _lib.AszError("no CUDA device: the native network has no CPU fallback")
         self.device = torch.device(device)
