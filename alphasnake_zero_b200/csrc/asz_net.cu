@@ -626,44 +626,77 @@ __global__ void im2col_kernel(const float* __restrict__ planes, int n_img, int r
   }
 }
 
-// ---- dense head: Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54), IMG images per CTA ----------------
-// thread t owns hidden unit t for all IMG images, so one pass over the 226 KB (11x11) of dense1 weights serves IMG images
-template <int IMG>
-__global__ void __launch_bounds__(128) dense_head_kernel(const float* __restrict__ head /* [P_tot] */, int n_img, int real, int pitch,
-                                                         int img_stride, const float* __restrict__ w1 /* [real*real][128] */,
+// ---- dense head: Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54), 8 images per CTA ------------------
+// The dense1 weights are re-laid out once on the padded raster ([img_stride][128], zero rows at padding positions), so the
+// head activations of an image are one contiguous run of img_stride floats (the epilogue wrote zeros at the padding).
+// 256 threads: thread t owns hidden units 2 (t % 64), +1 for all 8 images over one quarter of the raster (t / 64); one pass
+// over the weights serves 8 images; the four quarters are added in a fixed order (batch invariant).
+constexpr int kHeadImg = 8;
+__global__ void __launch_bounds__(256) dense_head_kernel(const float* __restrict__ head /* [P_tot] */, int n_img, int img_stride,
+                                                         const float* __restrict__ w1r /* [img_stride][128] */,
                                                          const float* __restrict__ b1, const float* __restrict__ w2 /* [128][3] */,
                                                          const float* __restrict__ b2, float* __restrict__ out /* [n][3] */) {
-  extern __shared__ float sh[];          // [IMG][real*real] inputs, then [IMG][128] hidden
-  const int rr = real * real;
+  extern __shared__ __align__(16) float sh[];          // [img_stride][8] inputs, [4][8][128] partial sums
   float* s_in = sh;
-  float* s_h = sh + IMG * rr;
-  const int n0 = (int)blockIdx.x * IMG, tid = (int)threadIdx.x;
-  for (int i = tid; i < IMG * rr; i += 128) {
-    const int j = i / rr, r = i - j * rr;
-    const int y = r / real, x = r - y * real;
-    s_in[i] = (n0 + j < n_img) ? head[kGuard + (size_t)(n0 + j) * img_stride + y * pitch + x] : 0.0f;
+  float* s_h = sh + kHeadImg * img_stride;
+  const int n0 = (int)blockIdx.x * kHeadImg, tid = (int)threadIdx.x;
+  const int up = tid & 63, quarter = tid >> 6;          // hidden units 2 up, 2 up + 1 over one quarter of the raster
+  const float* src = head + kGuard + (size_t)n0 * img_stride;
+  const int n_here = min(kHeadImg, n_img - n0);
+  for (int i = tid; i < kHeadImg * img_stride; i += 256) {
+    const int j = i / img_stride, r = i - j * img_stride;
+    s_in[r * kHeadImg + j] = j < n_here ? src[i] : 0.0f;
   }
   __syncthreads();
-  float acc[IMG];
+  float a0[kHeadImg], a1[kHeadImg];
 #pragma unroll
-  for (int j = 0; j < IMG; ++j) acc[j] = b1[tid];
-  for (int i = 0; i < rr; ++i) {
-    const float w = w1[(size_t)i * 128 + tid];
+  for (int j = 0; j < kHeadImg; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
+  const int qlen = (img_stride + 3) / 4;
+  const int i_begin = quarter * qlen, i_end = min(img_stride, i_begin + qlen);
+#pragma unroll 8
+  for (int i = i_begin; i < i_end; ++i) {
+    const float2 w = *reinterpret_cast<const float2*>(w1r + (size_t)i * 128 + 2 * up);
+    const float4 a = *reinterpret_cast<const float4*>(s_in + i * kHeadImg);
+    const float4 b = *reinterpret_cast<const float4*>(s_in + i * kHeadImg + 4);
+    const float x[kHeadImg] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int j = 0; j < IMG; ++j) acc[j] = fmaf(s_in[j * rr + i], w, acc[j]);
+    for (int j = 0; j < kHeadImg; ++j) { a0[j] = fmaf(x[j], w.x, a0[j]); a1[j] = fmaf(x[j], w.y, a1[j]); }
   }
 #pragma unroll
-  for (int j = 0; j < IMG; ++j) s_h[j * 128 + tid] = fmaxf(acc[j], 0.0f);
+  for (int j = 0; j < kHeadImg; ++j) {
+    *reinterpret_cast<float2*>(s_h + (quarter * kHeadImg + j) * 128 + 2 * up) = make_float2(a0[j], a1[j]);
+  }
   __syncthreads();
-  if (tid < IMG * 3) {
+  if (tid < 128) {
+#pragma unroll
+    for (int j = 0; j < kHeadImg; ++j) {
+      float v = b1[tid];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v += s_h[(q * kHeadImg + j) * 128 + tid];     // fixed order: batch invariant
+      s_h[j * 128 + tid] = fmaxf(v, 0.0f);
+    }
+  }
+  __syncthreads();
+  if (tid < kHeadImg * 3) {
     const int j = tid / 3, k = tid - j * 3;
-    if (n0 + j < n_img) {
+    if (j < n_here) {
       float o = b2[k];
       for (int u = 0; u < 128; ++u) o = fmaf(s_h[j * 128 + u], w2[u * 3 + k], o);
       out[(size_t)(n0 + j) * 3 + k] = tanhf(o);
     }
   }
 }
+
+// dense1 weights [real*real][128] -> padded raster [img_stride][128]
+__global__ void dense1_raster_kernel(const float* __restrict__ w1, int real, int pitch, int img_stride, float* __restrict__ w1r) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= img_stride * 128) return;
+  const int pos = i >> 7, u = i & 127;
+  const int y = pos / pitch, x = pos - y * pitch;
+  w1r[i] = (y < real && x < real) ? w1[((size_t)y * real + x) * 128 + u] : 0.0f;
+}
+
+
 
 
 template <int HALO, bool PAIR, bool FIRST>
@@ -714,6 +747,7 @@ struct asz_net {
   __nv_bfloat16* act[3] = {nullptr, nullptr, nullptr};
   __nv_bfloat16* col = nullptr;   // im2col input of the first layer [4][P_tot][8]
   float* head = nullptr;          // [P_tot]
+  float* w1r = nullptr;           // dense1 weights on the padded raster [img_stride][128]
   int n_sm = 148;
   int variant = 3;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_umma_kernel, one CTA per SM),
                                   // 3 = persistent over CTA pairs (conv_umma_kernel PAIR, cta_group::2)
@@ -755,7 +789,10 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
     if (v && v[0] >= '1' && v[0] <= '3') n->variant = v[0] - '0';
   }
   { int rc = configure_umma_kernels(); if (rc != ASZ_OK) { delete n; return rc; } }
-  ASZ_CUDA(cudaFuncSetAttribute(dense_head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  ASZ_CUDA(cudaFuncSetAttribute(dense_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  ASZ_CUDA(cudaMalloc(&n->w1r, (size_t)n->img_stride * 128 * sizeof(float)));
+  dense1_raster_kernel<<<(n->img_stride * 128 + 255) / 256, 256>>>(w->dense1_w, n->real, n->pitch, n->img_stride, n->w1r);
+  ASZ_CUDA(cudaGetLastError());
   for (int l = 0; l < 9; ++l) {
     const int taps = l == 0 ? 1 : 9, kc_in = l == 0 ? 4 : kKC;
     const int total = taps * kc_in * kC;
@@ -771,7 +808,7 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
 int asz_net_destroy(asz_net* n) {
   if (!n) return ASZ_OK;
   for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
-  cudaFree(n->col); cudaFree(n->head);
+  cudaFree(n->col); cudaFree(n->head); cudaFree(n->w1r);
   for (int l = 0; l < 9; ++l) cudaFree(n->w_pair[l]);
   delete n;
   return ASZ_OK;
@@ -869,12 +906,8 @@ static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, fl
       if (stop_layer == 2 + 2 * b) return last ? dump(nullptr, n->head, m) : dump(n->act[y], nullptr, m);
       x = y;
     }
-    {
-      constexpr int IMG = 8;
-      const size_t sh = (size_t)IMG * (n->real * n->real + 128) * sizeof(float);
-      dense_head_kernel<IMG><<<(m + IMG - 1) / IMG, 128, sh, st>>>(n->head, m, n->real, n->pitch, n->img_stride, n->w.dense1_w, n->w.dense1_b,
-                                                                  n->w.dense2_w, n->w.dense2_b, d_values + (size_t)i0 * 3);
-    }
+    dense_head_kernel<<<(m + kHeadImg - 1) / kHeadImg, 256, (size_t)kHeadImg * (n->img_stride + 4 * 128) * sizeof(float), st>>>(
+        n->head, m, n->img_stride, n->w1r, n->w.dense1_b, n->w.dense2_w, n->w.dense2_b, d_values + (size_t)i0 * 3);
     if (!cuda_ok(cudaGetLastError(), "dense_head_kernel")) return ASZ_ERR_CUDA;
   }
   return ASZ_OK;

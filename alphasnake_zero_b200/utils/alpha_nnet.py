@@ -1,9 +1,9 @@
 """AlphaNNet -- mirror of code/utils/alpha_nnet.py:8-109 (value network holder).
 
 On the hot path only `v` matters (alpha_nnet.py:61-76): batched forward + obstacle mask.  The forward runs either
-through the hand-written sm_100a kernels of libasz_b200.so (backend "native": implicit-GEMM convolutions on tcgen05
-tensor cores, bf16 operands, fp32 accumulation) or through plain PyTorch ops (backend "torch": the library baseline
-and fp32 reference used by the numerics tests).  Weights are kept in the Keras layouts the reference's .h5 files use
+through the hand-written sm_100a kernels of libasz_b200.so (backend "native", the default: implicit-GEMM convolutions on
+tcgen05 tensor cores, bf16 operands, fp32 accumulation; it raises when the library or a GPU is missing) or, only when asked
+for by name, through plain PyTorch ops (backend "torch": the library baseline and fp32 reference of the numerics tests).  Weights are kept in the Keras layouts the reference's .h5 files use
 (conv kernels HWIO, dense (in, out), BN gamma/beta/moving_mean/moving_variance).
 """
 import numpy as np
@@ -132,24 +132,18 @@ class AlphaNNet:
         return torch.tanh(h @ t["dense2_w"] + t["dense2_b"])
 
     def v_device(self, planes):
-        """raw network outputs for device planes (no obstacle mask): the engine's value_fn."""
-        if self.backend in ("native", "auto"):
-            nat = self._get_native()
-            if nat is not None:
-                return nat.forward(planes)
-            if self.backend == "native":
-                raise RuntimeError("native network backend requested but not available")
-        return self.forward_torch(planes, torch.bfloat16 if self.dtype == "bf16" else torch.float32)
+        """raw network outputs for device planes (no obstacle mask): the engine's value_fn.
+        "native" (and "auto", its alias) is the product path: the hand-written kernels or an exception, never a silent
+        library fallback.  "torch" is the explicit PyTorch/cuDNN path used as numerics reference and library baseline."""
+        if self.backend == "torch":
+            return self.forward_torch(planes, torch.bfloat16 if self.dtype == "bf16" else torch.float32)
+        return self._get_native().forward(planes)
 
     def _get_native(self):
         if self._native is None:
-            try:
-                from ..net import NativeNet
-            except ImportError:
-                self._native = False
-            else:
-                self._native = NativeNet(self.weights, self.device)
-        return self._native or None
+            from ..net import NativeNet          # raises if libasz_b200.so is missing: no fallback
+            self._native = NativeNet(self.weights, self.device)
+        return self._native
 
     def _forward_host(self, X):
         X = np.ascontiguousarray(np.array(X, dtype=np.float32))

@@ -127,17 +127,20 @@ def selfplay_api_leg(rank, games, breadth, depth, turns):
             "api": "MPGameRunner(%d games).run(Agent(net, 2, True, %d, %d), max_turns=%d)" % (games, depth, breadth, turns)}
 
 
-def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True):
-    """configs[2] of BASELINE.json (scaled by --sp-games): self-play root turns with the search kernels and the
-    hand-written value network.  A simulation = one sub-game rollout (agent.py:37-56)."""
+NET_FLOPS = {11: 1043724288, 19: 3240040448}   # per evaluation, 2 * MAC, convolutions + dense
+
+
+def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True, side=SIDE, snakes=SNAKES, label="configs[2]"):
+    """configs[2] of BASELINE.json (also [3] and [4] per GPU through tools/bench_selfplay.py): self-play root turns with
+    the search kernels and the hand-written value network.  A simulation = one sub-game rollout (agent.py:37-56)."""
     import torch
     from alphasnake_zero_b200.engine import Engine
     from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
     from alphasnake_zero_b200 import _lib
-    eng = Engine(side=SIDE, snakes=SNAKES, health_dec=HEALTH_DEC, food_chance=CHANCE, games=games, seed=77 + rank,
+    eng = Engine(side=side, snakes=snakes, health_dec=HEALTH_DEC, food_chance=CHANCE, games=games, seed=77 + rank,
                  max_depth=depth, max_breadth=breadth, softmax_base=2.0, training=True)
     eng.reset()
-    net = AlphaNNet(input_shape=(2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0, backend="native") if use_net else None
+    net = AlphaNNet(input_shape=(2 * side - 1, 2 * side - 1, 3), seed=0, backend="native") if use_net else None
     vf = net.v_device if use_net else None
 
     def root_turn():
@@ -157,15 +160,15 @@ def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True):
     dt = e0.elapsed_time(e1) * 1e-3
     s1 = eng.search_stats()
     d = {k: s1[k] - s0[k] for k in ("evals", "node_visits", "subgames", "subgame_tics")}
-    out = {"workload": "configs[2]: %d games x breadth %d (%d sims/move), depth %d, base 2, %s, Q cache on" %
-                       (games, breadth, (breadth // min(8, breadth)) * min(8, breadth), depth,
+    out = {"workload": "%s: %dx%d board, %d snakes, %d games x breadth %d (%d sims/move), depth %d, base 2, %s, Q cache on" %
+                       (label, side, side, snakes, games, breadth, (breadth // min(8, breadth)) * min(8, breadth), depth,
                         "bf16 tcgen05 value net (random init)" if use_net else "stub value function (search kernels only)"),
            "root_turns": turns, "seconds": dt, "sims_per_sec": d["subgames"] / dt, "node_visits_per_sec": d["node_visits"] / dt,
            "nn_evals_per_sec": d["evals"] / dt, "subgame_tics_per_sec": d["subgame_tics"] / dt,
            "hit_rate": 1.0 - d["evals"] / max(d["node_visits"], 1), "evals_per_sim": d["evals"] / max(d["subgames"], 1),
            "table_overflow": s1["overflow"], "tag_collisions": s1["collisions"]}
     if use_net:
-        flops = 1043724288
+        flops = NET_FLOPS[side]
         out["net_tflops"] = d["evals"] * flops / dt / 1e12
         try:
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
