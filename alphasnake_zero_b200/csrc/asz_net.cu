@@ -6,15 +6,17 @@
 //   activations  bf16, "channel-chunk major": act[kc][pos][8] (kc = channel / 8), pos = flat position of a padded
 //                22x22 raster per image (21 real rows/cols + one zero row/col shared by neighbours), so that the
 //                input of tap (dy,dx) for output rows [m, m+128) is simply rows [m+s, m+s+128), s = (dy-1)*22+(dx-1);
-//   A operand    one halo tile (128 + 2*24 rows, all 16 channel chunks) per CTA, fetched once with cp.async.bulk and
-//                reused by all 9 taps through the shared-memory descriptor's start address (no-swizzle K-major core
+//   A operand    one halo tile (256 + 2*24 rows, all 16 channel chunks) per CTA and super-tile, fetched with cp.async.bulk
+//                and reused by all 9 taps through the shared-memory descriptor's start address (no-swizzle K-major core
 //                matrices: 8 rows x 16 B contiguous, SBO = 128 B => rows are linear, any row offset is legal);
-//   B operand    weights [tap][kc][cout][8] bf16 streamed tap by tap (32 KB) through a 3-stage mbarrier ring;
-//   D            128 x 128 fp32 accumulator in TMEM, 72 tcgen05.mma (M128 N128 K16) per tile issued by one thread;
-//   epilogue     4 warps read TMEM (tcgen05.ld 32x32b), apply the folded BatchNorm scale/bias, the residual add and
+//   B operand    weights [tap][kc][cout][8] bf16 streamed in half-tap chunks through an mbarrier ring (9 stages of 16 KB;
+//                16 stages of 8 KB per CTA of a pair, which holds only half of the output channels);
+//   D            two 128 x 128 fp32 accumulators per super-tile in TMEM (double buffered: 512 columns), 144 tcgen05.mma
+//                (M128 N128 K16, or M256 N128 K16 with cta_group::2 over a CTA pair) issued by one elected thread;
+//   epilogue     8 warps read TMEM (tcgen05.ld 32x32b), apply the folded BatchNorm scale/bias, the residual add and
 //                the ReLU (alpha_nnet.py:22-47), zero the padding positions and store bf16 in the same layout; the
 //                last convolution instead applies the 1x1 head convolution + BN + ReLU (alpha_nnet.py:49-50).
-//   dense head   Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54): one CTA per image, fp32.
+//   dense head   Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54): 8 images per CTA, fp32.
 #include <cuda_bf16.h>
 
 #include <algorithm>

@@ -130,7 +130,7 @@ def selfplay_api_leg(rank, games, breadth, depth, turns):
 NET_FLOPS = {11: 1043724288, 19: 3240040448}   # per evaluation, 2 * MAC, convolutions + dense
 
 
-def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True, side=SIDE, snakes=SNAKES, label="configs[2]"):
+def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True, side=SIDE, snakes=SNAKES, label="configs[2]", prewarm_tics=32):
     """configs[2] of BASELINE.json (also [3] and [4] per GPU through tools/bench_selfplay.py): self-play root turns with
     the search kernels and the hand-written value network.  A simulation = one sub-game rollout (agent.py:37-56)."""
     import torch
@@ -140,6 +140,11 @@ def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True, side=SI
     eng = Engine(side=side, snakes=snakes, health_dec=HEALTH_DEC, food_chance=CHANCE, games=games, seed=77 + rank,
                  max_depth=depth, max_breadth=breadth, softmax_base=2.0, training=True)
     eng.reset()
+    # games of every age: uniform-random play with in-place reset first, so that the timed root turns see the live-snake
+    # mix of running self-play (fresh games only: all snakes alive => the shallowest searches, agent.py:45)
+    for _ in range(prewarm_tics):
+        eng.step(spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=False, auto_reset=True, random_actions=True)
+    live = float(eng.alive_mask().float().sum().item()) / games
     net = AlphaNNet(input_shape=(2 * side - 1, 2 * side - 1, 3), seed=0, backend="native") if use_net else None
     vf = net.v_device if use_net else None
 
@@ -166,7 +171,8 @@ def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True, side=SI
            "root_turns": turns, "seconds": dt, "sims_per_sec": d["subgames"] / dt, "node_visits_per_sec": d["node_visits"] / dt,
            "nn_evals_per_sec": d["evals"] / dt, "subgame_tics_per_sec": d["subgame_tics"] / dt,
            "hit_rate": 1.0 - d["evals"] / max(d["node_visits"], 1), "evals_per_sim": d["evals"] / max(d["subgames"], 1),
-           "table_overflow": s1["overflow"], "tag_collisions": s1["collisions"]}
+           "table_overflow": s1["overflow"], "tag_collisions": s1["collisions"],
+           "start_state": "%d uniform-random tics with in-place reset before the search starts: %.2f live snakes per game" % (prewarm_tics, live)}
     if use_net:
         flops = NET_FLOPS[side]
         out["net_tflops"] = d["evals"] * flops / dt / 1e12
@@ -202,33 +208,39 @@ def cpu_selfplay_baseline(games=8, breadth=50, depth=8):
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the reference's CPU implementation of the same path (its C port, oracle/asz_oracle.c -- the
+    reference itself is Python + TensorFlow and does not exist on the GPU box) on all host threads.
+    One step = the 65,536 env steps of the GPU arm's step, run as 8,192 persistent games x 8 tics (a bounded sample of
+    the games, the same number of tics + plane encodes)."""
     if rank != 0:
         return
     from oracle import oracle as orc
     orc.build()
     cores = os.cpu_count() or 1
-    g = 8192
+    g, tics = 8192, GAMES // 8192
     games = []
     for gi in range(g):
         og = orc.OracleGame(SIDE, SIDE, SNAKES, HEALTH_DEC)
         og.init_native(0, gi, 0)
         games.append(og)
+    arr = orc.env_handles(games)
     for _ in range(args.warmup):
-        orc.env_run(g, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, 1, encode=True, n_threads=cores, games=games)
+        orc.env_run(g, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, tics, encode=True, n_threads=cores, games=arr)
     t0 = time.time()
     steps = planes = 0
     for _ in range(args.steps):
-        st = orc.env_run(g, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, 1, encode=True, n_threads=cores, games=games)
+        st = orc.env_run(g, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, tics, encode=True, n_threads=cores, games=arr)
         steps += st["steps"]; planes += st["planes"]
     dt = time.time() - t0
     v = steps / dt
-    sample = "%d of the %d games per step, all %d host threads, C port of the reference (oracle/asz_oracle.c)" % (g, GAMES, cores)
-    print(json.dumps({
+    sample = "%d games x %d tics per step (= the %d env steps of one GPU step), all %d host threads, C port of the reference " \
+             "(oracle/asz_oracle.c)" % (g, tics, GAMES, cores)
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16/f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 11x11, 4 snakes, lockstep games, uniform-random actions, tic + fp32 plane encode",
-                   "games_per_step": g, "planes_per_step": planes / max(steps, 1)},
+                   "games_per_step": g, "tics_per_step": tics, "planes_per_step": planes / max(steps, 1)},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -381,12 +393,29 @@ def run_ours(args, rank, world, local_rank):
                 out["mcts_cpu_baseline"] = cpu_selfplay_baseline()
             except Exception as ex:
                 out["mcts_cpu_baseline"] = {"error": repr(ex)}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """the ONE JSON line goes to the process's original stdout; everything libraries print (NCCL's version banner,
+    warnings) was redirected to stderr in main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)          # fd 1 now points at stderr for every library in this process
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -178,12 +178,17 @@ def obstacle_mask(plane, H, W, v):
 def env_run(G, H=11, W=11, S=4, health_dec=1, chance=0.15, seed=0, tics=100, encode=True, n_threads=1, games=None):
     st = EnvStats()
     arr = None
-    if games is not None:
-        arr = (C.c_void_p * G)(*[g.h for g in games])
+    if games is not None:   # a list of OracleGame, or the ctypes array env_handles() made of one (reused between calls)
+        arr = games if isinstance(games, C.Array) else (C.c_void_p * G)(*[g.h for g in games])
     lib().oenv_run(arr, G, H, W, S, health_dec, chance_threshold(chance), seed, tics, int(bool(encode)), n_threads,
                    C.byref(st))
     return dict(steps=st.steps, planes=st.planes, episodes=st.episodes, plane_checksum=st.plane_checksum,
                 counters=list(st.counters))
+
+
+def env_handles(games):
+    """ctypes array of the games' handles, to be passed as env_run(games=...) repeatedly without rebuilding it"""
+    return (C.c_void_p * len(games))(*[g.h for g in games])
 
 
 def softermax(z, base):

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--world", type=int, default=0, help="GPUs the configuration is sharded over (default: the config's own)")
     ap.add_argument("--turns", type=int, default=2)
     ap.add_argument("--stub", action="store_true", help="stub value function (search kernels only)")
+    ap.add_argument("--prewarm-tics", type=int, default=32, help="uniform-random tics (with reset) before the search starts")
     args = ap.parse_args()
     import torch
     rank = int(os.environ.get("RANK", "0")); nproc = int(os.environ.get("WORLD_SIZE", "1"))
@@ -40,7 +41,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
         dist.barrier()
     r = bench.selfplay_leg(rank, games, c["breadth"], 8, args.turns, 1, use_net=not args.stub, side=c["side"], snakes=c["snakes"],
-                           label="%s, 1/%d of the games per GPU" % (c["label"], world))
+                           label="%s, 1/%d of the games per GPU" % (c["label"], world), prewarm_tics=args.prewarm_tics)
     r["ranks_run"] = nproc
     if nproc > 1:
         rates = ("sims_per_sec", "node_visits_per_sec", "nn_evals_per_sec", "subgame_tics_per_sec")
