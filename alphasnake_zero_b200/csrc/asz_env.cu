@@ -126,19 +126,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
     m.body = __shfl_sync(kFull, pf_meta, 3); m.headc = __shfl_sync(kFull, pf_meta, 4); m.starve = __shfl_sync(kFull, pf_meta, 5);
     m.eaten = __shfl_sync(kFull, pf_meta, 6); m.flags = __shfl_sync(kFull, pf_meta, 7);
     __syncwarp();
+    int row = 0, n_rows = 0;
+    unsigned live_mask = 0;
     if ((p.flags & ASZ_STEP_TIC) && !(m.flags & 1u)) {
       int move = 1;
+      uint32_t spawn_r[2] = {0u, 0u};
+      const bool merged_rng = (p.flags & ASZ_STEP_RANDOM_ACT) && p.spawn_mode == ASZ_SPAWN_NATIVE;
       if (p.flags & ASZ_STEP_RANDOM_ACT) {
+        // one SIMT pass draws the action streams (lanes 0..3 RS_ACT_LO, 4..7 RS_ACT_HI) and, in lanes >= 8, this tic's
+        // RS_SPAWN block: same streams and counters as separate calls, one Philox instead of two per game
         uint32_t r[4];
-        philox4x32_10((uint32_t)g, m.episode, (lane & 4) ? RS_ACT_HI : RS_ACT_LO, m.turn, p.seed, r);
+        const uint32_t stream = lane >= 8 ? (uint32_t)RS_SPAWN : (lane & 4) ? (uint32_t)RS_ACT_HI : (uint32_t)RS_ACT_LO;
+        philox4x32_10((uint32_t)g, m.episode, stream, m.turn, p.seed, r);
         const uint32_t rv = (lane & 3) == 0 ? r[0] : (lane & 3) == 1 ? r[1] : (lane & 3) == 2 ? r[2] : r[3];
         move = (int)mulhi32(rv, 3u);
+        spawn_r[0] = __shfl_sync(kFull, r[0], 8); spawn_r[1] = __shfl_sync(kFull, r[1], 8);
       } else if (lane < 8) {
         move = (int)p.actions[(size_t)g * 8 + lane];
       }
       const int spawn_cell = (p.spawn_mode == ASZ_SPAWN_REPLAY) ? p.spawn_cells[g] : -1;
       const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, p.spawn_mode, spawn_cell, p.chance_thresh, p.seed,
-                                      (uint32_t)g, p.S);
+                                      (uint32_t)g, p.S, merged_rng ? spawn_r : nullptr);
       if (p.rewards != nullptr && lane < 8)
         p.rewards[(size_t)g * 8 + lane] = (int8_t)(sn.reward == 1 ? 1 : sn.reward == 2 ? -1 : 0);
       if (lane == 0) {
@@ -150,6 +158,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         }
       }
       if (r.ended && (p.flags & ASZ_STEP_AUTO_RESET)) warp_init_native<G>(sb, sn, m, p.S, p.seed, (uint32_t)g, m.episode + 1);
+      // rows of this game: one atomicAdd per warp, issued before the write-back so that its latency is covered
+      if (enc && !(m.flags & 1u)) {
+        live_mask = __ballot_sync(kFull, sn.alive != 0);
+        n_rows = __popc(live_mask);
+        if (lane == 0 && n_rows > 0) { row = atomicAdd(p.row_count, n_rows); s_wtot[warp][8] += (uint32_t)n_rows; }
+      }
       // write the record back
       {
         uint32_t* gc = reinterpret_cast<uint32_t*>(p.cells + (size_t)g * G::PC);
@@ -165,19 +179,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       }
       if (lane < 8) p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
       store_meta(p.meta + (size_t)g * 8, m, lane);
-    } else if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) {
-      p.ended[g] = 0;
+    } else {
+      if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) p.ended[g] = 0;
+      if (enc && !(m.flags & 1u)) {
+        live_mask = __ballot_sync(kFull, sn.alive != 0);
+        n_rows = __popc(live_mask);
+        if (lane == 0 && n_rows > 0) { row = atomicAdd(p.row_count, n_rows); s_wtot[warp][8] += (uint32_t)n_rows; }
+      }
     }
     // the next game's record streams in while this game's planes are encoded
     nxt = __shfl_sync(kFull, nxt, 0);
     if (nxt < p.G) prefetch(nxt);
-    // ---- rows of this game: one atomicAdd per warp (rows of a game stay contiguous, ascending snake id) ----
-    if (enc && !(m.flags & 1u)) {
-      const unsigned live_mask = __ballot_sync(kFull, sn.alive != 0);
-      const int n_rows = __popc(live_mask);
+    // ---- planes of this game (rows of a game stay contiguous, ascending snake id) ----
+    {
       if (n_rows > 0) {
-        int row = 0;
-        if (lane == 0) { row = atomicAdd(p.row_count, n_rows); s_wtot[warp][8] += (uint32_t)n_rows; }
         CellView<G> cv;
         warp_cell_view<G>(sb, sn, cv, s_lut);
         row = __shfl_sync(kFull, row, 0);
@@ -319,7 +334,7 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
   if (rc != ASZ_OK) { delete e; return rc; }
   ASZ_CUDA(cudaMalloc(&e->planes, rows * (size_t)e->plane * sizeof(float) + 16));
   ASZ_CUDA(cudaMalloc(&e->row_ids, rows * sizeof(int32_t)));
-  ASZ_CUDA(cudaMalloc(&e->row_count, 2 * sizeof(int32_t)));   // [0] rows of the last step, [1] work counter
+  ASZ_CUDA(cudaMalloc(&e->row_count, 64 * sizeof(int32_t)));  // [0] rows of the last step, [32] work counter (own 128-byte line)
   ASZ_CUDA(cudaMalloc(&e->actions, G * 8));
   ASZ_CUDA(cudaMalloc(&e->spawn_cells, G * sizeof(int32_t)));
   ASZ_CUDA(cudaMalloc(&e->ended, G));
@@ -377,8 +392,8 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.planes = a->d_planes; p.row_ids = a->d_row_ids; p.keys = a->d_keys; p.max_rows = a->max_rows;
   p.row_count = a->d_row_count ? a->d_row_count : e->row_count;
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals;
-  p.work_counter = e->row_count + 1;
-  ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, 2 * sizeof(int32_t), st));
+  p.work_counter = e->row_count + 32;
+  ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, 64 * sizeof(int32_t), st));
   if (p.row_count != e->row_count) ASZ_CUDA(cudaMemsetAsync(p.row_count, 0, sizeof(int32_t), st));
   switch (e->cfg.side) {
     case 7: return EnvLaunch<7>::step(p, st);

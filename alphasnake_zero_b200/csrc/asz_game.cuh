@@ -105,9 +105,11 @@ __device__ __forceinline__ void warp_init_native(uint16_t* sb, Snake& sn, Meta& 
 // move: this lane's relative move (0 left, 1 straight, 2 right), read only where sn.alive.
 // spawn_mode 0: none (sub-games, game.py:268), 1: replay (spawn_cell or -1), 2: native Philox.
 template <class G>
+// spawn_r (optional): the two RS_SPAWN draws of this tic when the caller already has them (the env kernel computes them
+// in the same SIMT pass as the random actions); nullptr = drawn here.
 __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, int move, int health_dec, int spawn_mode,
                                               int spawn_cell, uint32_t chance_thresh, uint64_t seed, uint32_t game_id,
-                                              int S = kMaxSnakes) {
+                                              int S = kMaxSnakes, const uint32_t* spawn_r = nullptr) {
   constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS;
   const int lane = lane_id();
   const bool was_alive = sn.alive != 0;
@@ -167,9 +169,10 @@ __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, 
     __syncwarp();
   } else if (spawn_mode == 2) {
     uint32_t r[4];
-    philox4x32_10(game_id, m.episode, RS_SPAWN, m.turn, seed, r);
-    const int tot_food = warp_sum_i32(n_food);
-    if (tot_food == 0 || r[0] <= chance_thresh) {
+    if (spawn_r != nullptr) { r[0] = spawn_r[0]; r[1] = spawn_r[1]; }
+    else philox4x32_10(game_id, m.episode, RS_SPAWN, m.turn, seed, r);
+    const bool no_food = !__any_sync(kFull, n_food > 0);
+    if (no_food || r[0] <= chance_thresh) {
       const int pre = warp_excl_scan_i32(n_empty, lane);
       const int tot_empty = __shfl_sync(kFull, pre + n_empty, 31);
       if (tot_empty > 0) {
@@ -201,13 +204,13 @@ __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, 
     if (shared) { if (lose) cause = 3; }
     else if (sn.health <= 0) cause = 4;
   }
-  m.wall += (uint32_t)__popc(__ballot_sync(kFull, cause == 1));
-  m.body += (uint32_t)__popc(__ballot_sync(kFull, cause == 2));
-  m.headc += (uint32_t)__popc(__ballot_sync(kFull, cause == 3));
-  m.starve += (uint32_t)__popc(__ballot_sync(kFull, cause == 4));
   const unsigned dead_mask = __ballot_sync(kFull, cause != 0);
   // 6. remove (game.py:167-192): the dead snake's stamps are cleared, its head was never stamped
   if (dead_mask) {
+    m.wall += (uint32_t)__popc(__ballot_sync(kFull, cause == 1));
+    m.body += (uint32_t)__popc(__ballot_sync(kFull, cause == 2));
+    m.headc += (uint32_t)__popc(__ballot_sync(kFull, cause == 3));
+    m.starve += (uint32_t)__popc(__ballot_sync(kFull, cause == 4));
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
       const uint32_t v = sb[lane * CPL + q];
