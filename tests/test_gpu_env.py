@@ -133,7 +133,8 @@ def test_edge_cases_against_reference():
 
 
 @pytest.mark.parametrize("side,S,dec,G,tics", [(11, 4, 1, 4096, 120), (7, 4, 9, 1024, 80), (19, 8, 1, 512, 150),
-                                               (11, 2, 3, 1000, 60), (7, 8, 1, 333, 60)])
+                                               (11, 2, 3, 1000, 60), (7, 8, 1, 333, 60),
+                                               (11, 4, 1, 65536, 24)])      # BASELINE.json configs[1] at full size
 def test_native_run_against_oracle(side, S, dec, G, tics):
     """Seeded native runs (engine RNG for layouts, actions and food; auto reset): every game's final state, the
     totals and an order-free checksum over every plane written must equal the oracle's, bit for bit."""
