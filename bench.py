@@ -342,6 +342,26 @@ def run_ours(args, rank, world, local_rank):
             except Exception as ex:
                 sp["mcts_e2e"] = {"error": repr(ex)}
 
+    # ---- per-generation weight broadcast (the only collective of the design, outside the hot loop) ------
+    bcast = None
+    if world > 1:
+        from alphasnake_zero_b200.utils.alpha_nnet import flatten_weights, init_weights
+        n_par = sum(a.size for a in flatten_weights(init_weights((2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0)))
+        flat = torch.zeros(n_par, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            dist.broadcast(flat, src=0)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(10):
+            dist.broadcast(flat, src=0)
+        b1.record()
+        barrier()
+        t = torch.tensor([b0.elapsed_time(b1) / 10.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bcast = {"bytes": int(n_par * 4), "ms": float(t[0]), "what": "torch.distributed.broadcast (NCCL) of all weights and BN "
+                 "buffers of the value network, once per generation, not inside any timed region above"}
+
     # ---- reduce over ranks: max time, sum of work ----------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -386,6 +406,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": K, "clocks": clocks,
     }
     out.update(sp)
+    if bcast is not None:
+        out["weight_broadcast"] = bcast
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
         if not args.no_selfplay:
