@@ -61,6 +61,7 @@ SYMBOLS = [
     ("asz_search_finish", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ("asz_search_stub_values", C.c_int, [_vp, _vp]),
     ("asz_search_run_stub", C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    ("asz_search_run_net", C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     ("asz_obstacle_mask", C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     ("asz_debug_policy", C.c_int, [_vp, _vp, _i32, C.c_float, _vp, _vp, _vp, _vp]),
     ("asz_search_clear", C.c_int, [_vp, _vp]),

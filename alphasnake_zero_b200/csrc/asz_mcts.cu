@@ -744,6 +744,30 @@ int asz_search_run_stub(asz_engine* e, uint8_t* d_trace, int32_t trace_mode, con
   return asz_search_finish(e, d_root_trace, nullptr, nullptr, stream);
 }
 
+// Whole root-turn search with the hand-written value network: the epoch / step loops of Agent.make_moves (agent.py:37-58)
+// run here in native code; the only host synchronisation is the miss count of each step (it sizes the network batch).
+int asz_search_run_net(asz_engine* e, asz_net* net, uint8_t* d_trace, int32_t trace_mode, const uint8_t* d_root_trace, void* stream) {
+  if (!net) { set_error("asz_search_run_net: null network"); return ASZ_ERR_ARG; }
+  int rc = asz_search_begin(e, stream);
+  if (rc != ASZ_OK) return rc;
+  SearchState* s = e->search;
+  for (int ep = 0; ep < s->E; ++ep) {
+    if ((rc = asz_search_epoch_begin(e, stream)) != ASZ_OK) return rc;
+    for (int st = 1; st <= s->Dmax + 1; ++st) {
+      int32_t n_miss = 0;
+      if ((rc = asz_search_step_probe(e, &n_miss, stream)) != ASZ_OK) return rc;
+      if (st <= s->Dmax) {
+        if (n_miss > 0) {
+          if ((rc = asz_net_forward(net, s->eval_planes, n_miss, s->eval_values, stream)) != ASZ_OK) return rc;   // alpha_nnet.py:62
+          if ((rc = asz_obstacle_mask(e, s->eval_planes, n_miss, s->eval_values, stream)) != ASZ_OK) return rc;   // alpha_nnet.py:63-76
+        }
+        if ((rc = asz_search_step_sample(e, nullptr, d_trace, trace_mode, stream)) != ASZ_OK) return rc;
+      }
+    }
+  }
+  return asz_search_finish(e, d_root_trace, nullptr, nullptr, stream);
+}
+
 int asz_search_clear(asz_engine* e, void* stream) {
   if (!e || !e->search) { set_error("search is not configured"); return ASZ_ERR_STATE; }
   SearchState* s = e->search;

@@ -144,16 +144,20 @@ class Engine:
         holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
         return torch.as_tensor(holder, device=self.device).view(dtype).view(*shape)
 
-    def search(self, value_fn=None, trace=None, trace_mode=0, root_trace=None):
+    def search(self, value_fn=None, trace=None, trace_mode=0, root_trace=None, net=None):
         """One root turn of the search for the engine's current root games.
+        net: a NativeNet -- the whole root turn runs in one native call (asz_search_run_net), the product path.
         value_fn(planes[n, N, N, 3] float32 cuda) -> [n, 3] float32 cuda raw network outputs (the obstacle mask of
-        AlphaNNet.v is applied here); None = the deterministic stub value function (no host sync in the loops).
+        AlphaNNet.v is applied here): a Python-driven loop for reference networks (tests).
+        Neither = the deterministic stub value function (no host sync in the loops).
         trace: uint8 cuda tensor [epochs, max_steps, G*P, S]; trace_mode 0 none / 1 replay / 2 record.
         Returns (root_q [G, 8, 3] float32, root_moves [G, 8] uint8, 255 = no row) as views of engine buffers."""
         st = self.stream
         tp = C.c_void_p(trace.data_ptr()) if trace is not None else None
         rp = C.c_void_p(root_trace.data_ptr()) if root_trace is not None else None
-        if value_fn is None:
+        if net is not None:
+            check(self.L.asz_search_run_net(self.h, net.h, tp, trace_mode, rp, st))
+        elif value_fn is None:
             check(self.L.asz_search_run_stub(self.h, tp, trace_mode, rp, st))
         else:
             info = self.search_info()

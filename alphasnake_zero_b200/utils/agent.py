@@ -25,10 +25,13 @@ class Agent:
         if eng is None:
             raise TypeError("Agent.make_moves needs the games of an engine-backed MPGameRunner (no CPU path)")
         self._engine = eng
-        value_fn = None
+        value_fn = native = None
         if self.nnet is not None and not getattr(self.nnet, "is_stub", False):
-            value_fn = self.nnet.v_device
-        q, mv = eng.search(value_fn=value_fn)
+            if getattr(self.nnet, "backend", "native") == "torch":
+                value_fn = self.nnet.v_device          # explicit PyTorch reference network: Python-driven loop
+            else:
+                native = self.nnet._get_native()       # product path: the whole root turn in one native call
+        q, mv = eng.search(value_fn=value_fn, net=native)
         qh = q.cpu().numpy()
         mvh = mv.cpu().numpy()
         moves = [int(mvh[g, s]) for g, s in ids]

@@ -146,10 +146,10 @@ def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True, side=SI
         eng.step(spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=False, auto_reset=True, random_actions=True)
     live = float(eng.alive_mask().float().sum().item()) / games
     net = AlphaNNet(input_shape=(2 * side - 1, 2 * side - 1, 3), seed=0, backend="native") if use_net else None
-    vf = net.v_device if use_net else None
+    nat = net._get_native() if use_net else None
 
     def root_turn():
-        q, mv = eng.search(value_fn=vf)
+        q, mv = eng.search(net=nat)
         act = torch.where(mv < 3, mv, torch.ones_like(mv))
         eng.step(actions=act, spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=False, auto_reset=True)
     for _ in range(warm):

@@ -164,6 +164,11 @@ int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_
 int asz_search_stub_values(asz_engine* e, void* stream);
 /* the whole sequence above with the stub value function and no host synchronisation in the loops */
 int asz_search_run_stub(asz_engine* e, uint8_t* d_trace, int32_t trace_mode, const uint8_t* d_root_trace, void* stream);
+/* the whole sequence above with the value network of asz_net_create (declared below) as AlphaNNet.v: Agent.make_moves
+ * (agent.py:25-111) for one root turn in one call; the host only waits for each step's miss count */
+struct asz_net;
+int asz_search_run_net(asz_engine* e, struct asz_net* net, uint8_t* d_trace, int32_t trace_mode, const uint8_t* d_root_trace,
+                       void* stream);
 /* AlphaNNet.v's obstacle mask (alpha_nnet.py:63-76) applied in place to d_values [n][3] for d_planes [n][plane] */
 int asz_obstacle_mask(asz_engine* e, const float* d_planes, int32_t n, float* d_values, void* stream);
 /* test hook: Agent.softermax (agent.py:114-122), numpy.random.choice([0,1,2], p) for a given uniform draw u (float64),

@@ -246,3 +246,36 @@ def test_search_with_network_value_function_against_oracle():
             games[gi].tic(root[r0:r0 + n].astype(np.int32), spawn_mode=2, chance=0.15, seed=seed)
             r0 += n
     eng.close()
+
+
+def test_native_whole_turn_search_equals_python_driven_loop():
+    """asz_search_run_net (the product path: one native call per root turn) against the Python-driven step loop with the same
+    hand-written network as value function.  The native run records its sampled moves, the Python-driven run replays them
+    (W is summed with float atomics, so a 1-ulp difference could otherwise flip a draw): identical visit counts, keys,
+    evaluation counts; Q within float reassociation."""
+    import torch
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    net = AlphaNNet(input_shape=(21, 21, 3), seed=4, backend="native")
+    net.weights["dense2_w"] = (net.weights["dense2_w"] * 5).astype(np.float32)
+    nat = net._get_native()
+    G, S, D, B, seed = 48, 4, 8, 24, 5
+    ea = _engine(side=11, snakes=S, games=G, seed=seed, max_depth=D, max_breadth=B, softmax_base=2.0, training=True, table_log2=20)
+    eb = _engine(side=11, snakes=S, games=G, seed=seed, max_depth=D, max_breadth=B, softmax_base=2.0, training=True, table_log2=20)
+    ea.reset(); eb.reset()
+    info = ea.search_info()
+    for t in range(3):
+        tree = torch.full((info["epochs"], info["max_steps"], G * info["P"], S), 255, dtype=torch.uint8, device="cuda")
+        qa, ma = ea.search(net=nat, trace=tree, trace_mode=2)
+        qa, ma = qa.clone(), ma.clone()
+        qb, mb = eb.search(value_fn=nat.forward, trace=tree, trace_mode=1, root_trace=ma.reshape(-1).contiguous())
+        assert torch.equal(ma, mb)
+        np.testing.assert_allclose(qa.cpu().numpy(), qb.cpu().numpy(), rtol=0, atol=2e-5)
+        ta, tb = ea.table(), eb.table()
+        assert np.array_equal(ta["keys"], tb["keys"]) and np.array_equal(ta["N"], tb["N"])
+        np.testing.assert_allclose(ta["W"], tb["W"], rtol=0, atol=2e-4)
+        act = torch.where(ma < 3, ma, torch.ones_like(ma))
+        ea.step(actions=act, spawn_mode=2, tic=True, encode=False)
+        eb.step(actions=act, spawn_mode=2, tic=True, encode=False)
+    sa, sb = ea.search_stats(), eb.search_stats()
+    assert sa["evals"] == sb["evals"] > 0 and sa["node_visits"] == sb["node_visits"] and sa["subgames"] == sb["subgames"]
+    ea.close(); eb.close()
