@@ -88,6 +88,34 @@ __device__ __forceinline__ int warp_excl_scan_i32(int v, int lane) {
   return s - v;
 }
 
+// ---- L2 residency hints ---------------------------------------------------------------------------------------------
+// The game records (21 MB at 65,536 games) are read and rewritten by every launch and fit in L2 many times over; the
+// planes (1 GB per launch) stream through it.  Records are accessed with an evict_last policy, planes with evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint32_t ld_hint_u32(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_hint_u64(const uint64_t* p, uint64_t pol) {
+  uint64_t v;
+  asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint_u32(uint32_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_u64(uint64_t* p, uint64_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_v2u32(uint32_t* p, uint32_t a, uint32_t b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol) : "memory");
+}
+
 // streaming 16-byte store that does not allocate in L1 (planes are written once and read by another kernel)
 __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),

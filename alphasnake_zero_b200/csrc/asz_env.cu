@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   }
   __syncthreads();
   EncodeCtx<G> ctx;
-  ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg;
+  ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg; ctx.policy = l2_policy_evict_first();
 #pragma unroll
   for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
   __shared__ uint32_t s_wtot[WARPS][12];         // per-warp totals (only lane 0 of the warp touches its row)
@@ -104,11 +104,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   uint64_t pf_snake = 0;
   uint32_t pf_meta = 0;
   int g = (int)blockIdx.x * WARPS + warp;
+  const uint64_t keep = l2_policy_evict_last();
   auto prefetch = [&](int gi) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cells + (size_t)gi * G::PC);
 #pragma unroll
-    for (int q = 0; q < BW; ++q) pf_board[q] = src[lane * BW + q];
-    if (lane < 8) { pf_snake = p.snakes[(size_t)gi * 8 + lane]; pf_meta = p.meta[(size_t)gi * 8 + lane]; }
+    for (int q = 0; q < BW; ++q) pf_board[q] = ld_hint_u32(src + lane * BW + q, keep);
+    if (lane < 8) { pf_snake = ld_hint_u64(p.snakes + (size_t)gi * 8 + lane, keep); pf_meta = ld_hint_u32(p.meta + (size_t)gi * 8 + lane, keep); }
   };
   if (g < p.G) prefetch(g);
   while (g < p.G) {
@@ -170,15 +171,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         const uint32_t* src = reinterpret_cast<const uint32_t*>(sb);
         if constexpr (BW % 2 == 0) {
 #pragma unroll
-          for (int q = 0; q < BW / 2; ++q)
-            reinterpret_cast<uint2*>(gc)[lane * (BW / 2) + q] = reinterpret_cast<const uint2*>(src)[lane * (BW / 2) + q];
+          for (int q = 0; q < BW / 2; ++q) {
+            const uint2 v = reinterpret_cast<const uint2*>(src)[lane * (BW / 2) + q];
+            st_hint_v2u32(gc + 2 * (lane * (BW / 2) + q), v.x, v.y, keep);
+          }
         } else {
 #pragma unroll
-          for (int q = 0; q < BW; ++q) gc[lane * BW + q] = src[lane * BW + q];
+          for (int q = 0; q < BW; ++q) st_hint_u32(gc + lane * BW + q, src[lane * BW + q], keep);
         }
       }
-      if (lane < 8) p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
-      store_meta(p.meta + (size_t)g * 8, m, lane);
+      if (lane < 8) {
+        st_hint_u64(p.snakes + (size_t)g * 8 + lane, pack_snake(sn), keep);
+        const uint32_t mv = lane == 0 ? m.turn : lane == 1 ? m.episode : lane == 2 ? m.wall : lane == 3 ? m.body
+                          : lane == 4 ? m.headc : lane == 5 ? m.starve : lane == 6 ? m.eaten : m.flags;
+        st_hint_u32(p.meta + (size_t)g * 8 + lane, mv, keep);
+      }
     } else {
       if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) p.ended[g] = 0;
       if (enc && !(m.flags & 1u)) {

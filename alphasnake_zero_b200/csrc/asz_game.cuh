@@ -356,6 +356,7 @@ struct EncodeCtx {
   float* cur;            // staging buffer of the next plane
   float* oth;            // the other buffer (its bulk store may still be in flight)
   const float* bg;
+  uint64_t policy;       // L2 cache policy of the plane stores
   int prev_cur[G::CPL];  // stage index of the pixel each of this lane's cells was scattered to in `cur` (-1 none)
   int prev_oth[G::CPL];
 };
@@ -368,9 +369,16 @@ __device__ __forceinline__ void fill_wall_pattern(float* dst, int n_floats, int 
     reinterpret_cast<float4*>(dst)[q4] = v;
   }
 }
-__device__ __forceinline__ void bulk_s2g(float* gdst, const float* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+// L2 policy of the plane stores: planes are written once and read much later by another kernel (the batch is larger than
+// L2), so they should leave L2 first and not push the game records (read and rewritten every launch) out of it
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_s2g(float* gdst, const float* ssrc, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -449,9 +457,9 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   if (EE > eE) EE = eE;
   float* obase = out + gidx0;
   if (lane == 0) {
-    if (EA > eA) bulk_s2g(obase + eA, ctx.bg + 4 * (eA % 3), (uint32_t)((EA - eA) * 4));            // wall before the window
-    bulk_s2g(obase + EA, stage + (EA - W0 + off), (uint32_t)((EE - EA) * 4));                       // the window rows
-    if (eE > EE) bulk_s2g(obase + EE, ctx.bg + 4 * (EE % 3), (uint32_t)((eE - EE) * 4));            // wall after the window
+    if (EA > eA) bulk_s2g(obase + eA, ctx.bg + 4 * (eA % 3), (uint32_t)((EA - eA) * 4), ctx.policy);            // wall before the window
+    bulk_s2g(obase + EA, stage + (EA - W0 + off), (uint32_t)((EE - EA) * 4), ctx.policy);                       // the window rows
+    if (eE > EE) bulk_s2g(obase + EE, ctx.bg + 4 * (EE % 3), (uint32_t)((eE - EE) * 4), ctx.policy);            // wall after the window
     bulk_commit();
   } else if (lane <= 6) {
     // up to 3 floats before the first and after the last 16-byte boundary of the plane
