@@ -48,6 +48,7 @@ struct asz_engine {
   uint8_t* ended = nullptr;       // [G]
   int8_t* rewards = nullptr;      // [G*8]
   unsigned long long* totals = nullptr;  // [8]
+  int device_hints = 1, host_hints = 0, step_hints = 1;   // L2 policy hints of env_step_kernel (asz_env.cu)
   asz::SearchState* search = nullptr;
 };
 

@@ -33,6 +33,7 @@ struct EnvParams {
   float* planes; int32_t* row_ids; uint64_t* keys; int max_rows; int32_t* row_count;
   uint8_t* ended; int8_t* rewards; unsigned long long* totals;
   int* work_counter;   // dynamic game scheduler of the persistent kernel (zeroed before the launch)
+  int hints;           // 1: L2 policies (planes evict_first, game records evict_last), 0: default policy everywhere
 };
 
 // ---- record load / store ------------------------------------------------------------------------------------------
@@ -69,7 +70,10 @@ __device__ __forceinline__ void store_meta(uint32_t* gm, const Meta& m, int lane
 // ---- the fused step kernel ----------------------------------------------------------------------------------------
 // Persistent: MINB CTAs per SM, every warp loops over games g = warp_global, warp_global + n_warps, ... so that the
 // staging buffers' wall background is written once per warp and bulk stores of one game overlap the tic of the next.
-template <int SIDE, int WARPS, int MINB>
+// HINTS: plane stores carry an evict_first L2 policy and the game records (read and rewritten by every launch, 21 MB at
+// 65,536 games) an evict_last one.  Worth 4 % on the device-resident path; the host-buffer path (asz_env_step_host) runs
+// 25 % SLOWER with either hint (measured, tools/env_state_probe3.py), so it uses the plain instructions.
+template <int SIDE, int WARPS, int MINB, bool HINTS>
 __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvParams p) {
   using G = Geo<SIDE>;
   using E = EncGeo<G>;
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   }
   __syncthreads();
   EncodeCtx<G> ctx;
-  ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg; ctx.policy = l2_policy_evict_first();
+  ctx.cur = stage0; ctx.oth = stage0 + E::WSTAGE; ctx.bg = s_bg; ctx.policy = HINTS ? l2_policy_evict_first() : 0ull;
 #pragma unroll
   for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
   __shared__ uint32_t s_wtot[WARPS][12];         // per-warp totals (only lane 0 of the warp touches its row)
@@ -104,12 +108,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   uint64_t pf_snake = 0;
   uint32_t pf_meta = 0;
   int g = (int)blockIdx.x * WARPS + warp;
-  const uint64_t keep = l2_policy_evict_last();
+  const uint64_t keep = HINTS ? l2_policy_evict_last() : 0ull;
   auto prefetch = [&](int gi) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cells + (size_t)gi * G::PC);
 #pragma unroll
-    for (int q = 0; q < BW; ++q) pf_board[q] = ld_hint_u32(src + lane * BW + q, keep);
-    if (lane < 8) { pf_snake = ld_hint_u64(p.snakes + (size_t)gi * 8 + lane, keep); pf_meta = ld_hint_u32(p.meta + (size_t)gi * 8 + lane, keep); }
+    if constexpr (HINTS) {
+#pragma unroll
+      for (int q = 0; q < BW; ++q) pf_board[q] = ld_hint_u32(src + lane * BW + q, keep);
+      if (lane < 8) { pf_snake = ld_hint_u64(p.snakes + (size_t)gi * 8 + lane, keep); pf_meta = ld_hint_u32(p.meta + (size_t)gi * 8 + lane, keep); }
+    } else {
+#pragma unroll
+      for (int q = 0; q < BW; ++q) pf_board[q] = src[lane * BW + q];
+      if (lane < 8) { pf_snake = p.snakes[(size_t)gi * 8 + lane]; pf_meta = p.meta[(size_t)gi * 8 + lane]; }
+    }
   };
   if (g < p.G) prefetch(g);
   while (g < p.G) {
@@ -173,18 +184,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
 #pragma unroll
           for (int q = 0; q < BW / 2; ++q) {
             const uint2 v = reinterpret_cast<const uint2*>(src)[lane * (BW / 2) + q];
-            st_hint_v2u32(gc + 2 * (lane * (BW / 2) + q), v.x, v.y, keep);
+            if constexpr (HINTS) st_hint_v2u32(gc + 2 * (lane * (BW / 2) + q), v.x, v.y, keep);
+            else reinterpret_cast<uint2*>(gc)[lane * (BW / 2) + q] = v;
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < BW; ++q) st_hint_u32(gc + lane * BW + q, src[lane * BW + q], keep);
+          for (int q = 0; q < BW; ++q) {
+            if constexpr (HINTS) st_hint_u32(gc + lane * BW + q, src[lane * BW + q], keep);
+            else gc[lane * BW + q] = src[lane * BW + q];
+          }
         }
       }
       if (lane < 8) {
-        st_hint_u64(p.snakes + (size_t)g * 8 + lane, pack_snake(sn), keep);
         const uint32_t mv = lane == 0 ? m.turn : lane == 1 ? m.episode : lane == 2 ? m.wall : lane == 3 ? m.body
                           : lane == 4 ? m.headc : lane == 5 ? m.starve : lane == 6 ? m.eaten : m.flags;
-        st_hint_u32(p.meta + (size_t)g * 8 + lane, mv, keep);
+        if constexpr (HINTS) {
+          st_hint_u64(p.snakes + (size_t)g * 8 + lane, pack_snake(sn), keep);
+          st_hint_u32(p.meta + (size_t)g * 8 + lane, mv, keep);
+        } else {
+          p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
+          p.meta[(size_t)g * 8 + lane] = mv;
+        }
       }
     } else {
       if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) p.ended[g] = 0;
@@ -210,10 +230,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
           if (row < p.max_rows) {
             uint64_t k0 = 0, k1 = 0;
             if (p.flags & ASZ_STEP_KEYS) {
-              warp_encode_v2<G, true>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, &k0, &k1);
+              warp_encode_v2<G, true, HINTS>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, &k0, &k1);
               if (lane == 0) { p.keys[2 * (size_t)row] = k0; p.keys[2 * (size_t)row + 1] = k1; }
             } else {
-              warp_encode_v2<G, false>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
+              warp_encode_v2<G, false, HINTS>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
             }
             if (lane == 0) p.row_ids[row] = g * 8 + vs;
           }
@@ -258,15 +278,15 @@ struct EnvLaunch {
     return (size_t)(E::BGLEN + WARPS * 2 * E::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t) +
            (size_t)(G::PC + 8) * sizeof(float);
   }
-  template <int MINB>
+  template <int MINB, bool HINTS>
   static int launch(const EnvParams& p, cudaStream_t st) {
     static bool configured = false;
     static int n_sm = 0;
     if (!configured) {
-      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_bytes()), "cudaFuncSetAttribute(env_step_kernel)"))
         return ASZ_ERR_CUDA;
-      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
         return ASZ_ERR_CUDA;
       int dev = 0;
@@ -275,15 +295,15 @@ struct EnvLaunch {
       configured = true;
     }
     const int blocks = std::min((p.G + WARPS - 1) / WARPS, n_sm * MINB);
-    env_step_kernel<SIDE, WARPS, MINB><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
+    env_step_kernel<SIDE, WARPS, MINB, HINTS><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
     return cuda_ok(cudaGetLastError(), "env_step_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
   }
   static int step(const EnvParams& p, cudaStream_t st) {
-    static int minb = -1;
-    if (minb < 0) { const char* v = getenv("ASZ_ENV_MINB"); minb = v ? atoi(v) : 0; }
-    if (SIDE >= 19) return launch<2>(p, st);
-    if (minb == 4) return launch<4>(p, st);
-    return launch<3>(p, st);
+    // 3 CTAs x 8 warps per SM at 80 registers (2 x 4 at 19x19).  Measured alternatives at 11x11 (tools/env_sustain.py, us per
+    // launch of 65,536 games): 8 warps x 3 CTAs 176.8 | 12 x 2 176.8 | 10 x 2 177.3 | 8 x 2 196.2 (too few warps) |
+    // 7 x 4 206.6, 5 x 5 211.1, 6 x 5 227.2, 8 x 4 233 (register spills)
+    if (SIDE >= 19) return p.hints ? launch<2, true>(p, st) : launch<2, false>(p, st);
+    return p.hints ? launch<3, true>(p, st) : launch<3, false>(p, st);
   }
   static int reset(const GameSet& gs, int S, uint64_t seed, cudaStream_t st) {
     const int blocks = (gs.n + WARPS - 1) / WARPS;
@@ -331,6 +351,9 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
   }
   asz_engine* e = new asz_engine();
   e->cfg = *cfg;
+  { const char* v = getenv("ASZ_ENV_HINTS"); e->device_hints = v ? atoi(v) : 1; }            // experiments only
+  { const char* v = getenv("ASZ_ENV_HINTS_HOST"); e->host_hints = v ? atoi(v) : 0; }
+  e->step_hints = e->device_hints;
   ASZ_CUDA(cudaGetDevice(&e->device));
   e->pc = pc_of(cfg->side);
   e->plane = (2 * cfg->side - 1) * (2 * cfg->side - 1) * 3;
@@ -400,6 +423,7 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.row_count = a->d_row_count ? a->d_row_count : e->row_count;
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals;
   p.work_counter = e->row_count + 32;
+  p.hints = e->step_hints;
   ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, 64 * sizeof(int32_t), st));
   if (p.row_count != e->row_count) ASZ_CUDA(cudaMemsetAsync(p.row_count, 0, sizeof(int32_t), st));
   switch (e->cfg.side) {
@@ -428,10 +452,27 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
   a.flags = flags; a.spawn_mode = spawn_mode; a.d_actions = e->actions; a.d_spawn_cells = e->spawn_cells;
   a.d_planes = e->planes; a.d_row_ids = e->row_ids; a.max_rows = (int32_t)(G * (size_t)e->cfg.snakes);
   a.d_row_count = e->row_count; a.d_ended = e->ended; a.d_rewards = e->rewards;
+  // Result buffers in pinned (page-locked, UVA-mapped) host memory are written by the kernel itself, one posted PCIe write
+  // per game while the launch runs, instead of by two device->host copies after it (ASZ_HOST_ZEROCOPY=0 disables).
+  static int zero_copy = -1;
+  if (zero_copy < 0) { const char* v = getenv("ASZ_HOST_ZEROCOPY"); zero_copy = v ? atoi(v) : 1; }
+  bool zc_ended = false, zc_rewards = false;
+  if (zero_copy && (flags & ASZ_STEP_TIC)) {
+    cudaPointerAttributes at;
+    if (h_ended && cudaPointerGetAttributes(&at, h_ended) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      a.d_ended = static_cast<uint8_t*>(at.devicePointer); zc_ended = true;
+    }
+    if (h_rewards && cudaPointerGetAttributes(&at, h_rewards) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      a.d_rewards = static_cast<int8_t*>(at.devicePointer); zc_rewards = true;
+    }
+    cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers: not ours
+  }
+  e->step_hints = e->host_hints;
   int rc = asz_env_step(e, &a, stream);
+  e->step_hints = e->device_hints;
   if (rc != ASZ_OK) return rc;
-  if (h_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, e->ended, G, cudaMemcpyDeviceToHost, st));
-  if (h_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, e->rewards, G * 8, cudaMemcpyDeviceToHost, st));
+  if (h_ended && !zc_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, e->ended, G, cudaMemcpyDeviceToHost, st));
+  if (h_rewards && !zc_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, e->rewards, G * 8, cudaMemcpyDeviceToHost, st));
   int32_t rows = 0;
   ASZ_CUDA(cudaMemcpyAsync(&rows, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   ASZ_CUDA(cudaStreamSynchronize(st));

@@ -376,17 +376,24 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+template <bool kHint>
 __device__ __forceinline__ void bulk_s2g(float* gdst, const float* ssrc, uint32_t bytes, uint64_t policy) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
-               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(policy)
-               : "memory");
+  if constexpr (kHint) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(policy)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <class G, bool kWantKey>
+template <class G, bool kWantKey, bool kHint = false>
 __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snake& sn, int vs, EncodeCtx<G>& ctx, float* out,
                                                size_t gidx0, uint64_t* key0, uint64_t* key1) {
   constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS, N = G::N, PLANE = G::PLANE;
@@ -457,9 +464,9 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   if (EE > eE) EE = eE;
   float* obase = out + gidx0;
   if (lane == 0) {
-    if (EA > eA) bulk_s2g(obase + eA, ctx.bg + 4 * (eA % 3), (uint32_t)((EA - eA) * 4), ctx.policy);            // wall before the window
-    bulk_s2g(obase + EA, stage + (EA - W0 + off), (uint32_t)((EE - EA) * 4), ctx.policy);                       // the window rows
-    if (eE > EE) bulk_s2g(obase + EE, ctx.bg + 4 * (EE % 3), (uint32_t)((eE - EE) * 4), ctx.policy);            // wall after the window
+    if (EA > eA) bulk_s2g<kHint>(obase + eA, ctx.bg + 4 * (eA % 3), (uint32_t)((EA - eA) * 4), ctx.policy);            // wall before the window
+    bulk_s2g<kHint>(obase + EA, stage + (EA - W0 + off), (uint32_t)((EE - EA) * 4), ctx.policy);                       // the window rows
+    if (eE > EE) bulk_s2g<kHint>(obase + EE, ctx.bg + 4 * (EE % 3), (uint32_t)((eE - EE) * 4), ctx.policy);            // wall after the window
     bulk_commit();
   } else if (lane <= 6) {
     // up to 3 floats before the first and after the last 16-byte boundary of the plane

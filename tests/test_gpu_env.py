@@ -191,6 +191,29 @@ def test_env_step_host_roundtrip():
                                        C.c_void_p(planes.data_ptr()), C.c_void_p(ids.data_ptr()), eng.stream))
     n = rows.value
     assert 0 < n <= G * 4
+    # results written into pinned memory by the kernel (zero-copy), into pageable memory by copies, and the device-resident
+    # results of an identical engine stepped through asz_env_step must agree
+    ea, eb, ec = (_engine(side=11, snakes=4, games=256, seed=3) for _ in range(3))
+    for x in (ea, eb, ec):
+        x.reset()
+    end_pin = torch.zeros(G, dtype=torch.uint8).pin_memory(); rew_pin = torch.zeros(G, 8, dtype=torch.int8).pin_memory()
+    end_pg = np.zeros(G, np.uint8); rew_pg = np.zeros((G, 8), np.int8)
+    act_d = torch.ones(G, 8, dtype=torch.uint8, device="cuda")
+    r2 = C.c_int32(0)
+    seen_end = 0
+    for t in range(40):
+        _lib.check(L.asz_env_step_host(ea.h, _lib.STEP_TIC, 2, C.c_void_p(actions.data_ptr()), None, C.c_void_p(end_pin.data_ptr()),
+                                       C.c_void_p(rew_pin.data_ptr()), C.byref(r2), None, None, ea.stream))
+        _lib.check(L.asz_env_step_host(eb.h, _lib.STEP_TIC, 2, C.c_void_p(actions.data_ptr()), None, end_pg.ctypes.data_as(C.c_void_p),
+                                       rew_pg.ctypes.data_as(C.c_void_p), C.byref(r2), None, None, eb.stream))
+        ec.step(actions=act_d, spawn_mode=2, tic=True, encode=False)
+        torch.cuda.synchronize()
+        assert np.array_equal(end_pin.numpy(), end_pg) and np.array_equal(rew_pin.numpy(), rew_pg), t
+        assert np.array_equal(end_pg, ec.ended.cpu().numpy()) and np.array_equal(rew_pg, ec.rewards.cpu().numpy()), t
+        seen_end += int(end_pg.sum())
+    assert seen_end > 0
+    for x in (ea, eb, ec):
+        x.close()
     # all snakes went straight for 5 tics from a start cell next to the wall: planes must match get_state-derived oracle
     from oracle import oracle as orc
     order = np.argsort(ids[:n].numpy())
