@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libasz_b200.so")
+LIB_PATH = os.environ.get("ASZ_LIB") or os.path.join(HERE, "libasz_b200.so")   # ASZ_LIB: measurement builds (tools/)
 
 ASZ_MAX_SNAKES = 8
 STEP_TIC, STEP_ENCODE, STEP_AUTO_RESET, STEP_RANDOM_ACT, STEP_KEYS = 1, 2, 4, 8, 16
@@ -50,6 +50,7 @@ SYMBOLS = [
     ("asz_env_step", C.c_int, [_vp, C.POINTER(StepArgs), _vp]),
     ("asz_env_step_host", C.c_int, [_vp, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("asz_get_totals", C.c_int, [_vp, _vp]),
+    ("asz_internal_profile", C.c_int, [_vp, _vp]),
     ("asz_internal_state", C.c_int, [_vp, _vp]),
     ("asz_internal_planes", _vp, [_vp]),
     ("asz_internal_row_ids", _vp, [_vp]),

@@ -33,8 +33,18 @@ struct EnvParams {
   float* planes; int32_t* row_ids; uint64_t* keys; int max_rows; int32_t* row_count;
   uint8_t* ended; int8_t* rewards; unsigned long long* totals;
   int* work_counter;   // dynamic game scheduler of the persistent kernel (zeroed before the launch)
+  unsigned long long* prof;   // ASZ_ENV_PROFILE builds only: per-phase cycle sums (tools/env_profile.py)
   int hints;           // 1: L2 policies (planes evict_first, game records evict_last), 0: default policy everywhere
 };
+
+// Phase timers for the measurement build (nvcc -DASZ_ENV_PROFILE, tools/env_profile.py); they compile to nothing otherwise.
+#ifdef ASZ_ENV_PROFILE
+#define ASZ_PROF_DECL long long prof_t = clock64();
+#define ASZ_PROF(k) do { const long long prof_n = clock64(); if (lane == 0) s_prof[warp][k] += (unsigned long long)(prof_n - prof_t); prof_t = prof_n; } while (0)
+#else
+#define ASZ_PROF_DECL
+#define ASZ_PROF(k) do { } while (0)
+#endif
 
 // ---- record load / store ------------------------------------------------------------------------------------------
 template <class G>
@@ -98,6 +108,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
   __shared__ uint32_t s_wtot[WARPS][12];         // per-warp totals (only lane 0 of the warp touches its row)
   if (lane < 12) s_wtot[warp][lane] = 0u;
+#ifdef ASZ_ENV_PROFILE
+  __shared__ unsigned long long s_prof[WARPS][8];
+  if (lane < 8) s_prof[warp][lane] = 0ull;
+  ctx.prof_wait = &s_prof[warp][6];
+#endif
   __syncwarp();
 
   // dynamic scheduling: the first game of a warp is static, later ones come from a global counter that is fetched one
@@ -111,7 +126,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   const uint64_t keep = HINTS ? l2_policy_evict_last() : 0ull;
   auto prefetch = [&](int gi) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cells + (size_t)gi * G::PC);
-#pragma unroll
     if constexpr (HINTS) {
 #pragma unroll
       for (int q = 0; q < BW; ++q) pf_board[q] = ld_hint_u32(src + lane * BW + q, keep);
@@ -124,6 +138,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   };
   if (g < p.G) prefetch(g);
   while (g < p.G) {
+    ASZ_PROF_DECL
     int nxt = 0;
     if (lane == 0) nxt = n_warps + atomicAdd(p.work_counter, 1);
     {
@@ -138,6 +153,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
     m.body = __shfl_sync(kFull, pf_meta, 3); m.headc = __shfl_sync(kFull, pf_meta, 4); m.starve = __shfl_sync(kFull, pf_meta, 5);
     m.eaten = __shfl_sync(kFull, pf_meta, 6); m.flags = __shfl_sync(kFull, pf_meta, 7);
     __syncwarp();
+    ASZ_PROF(0);   // waiting for the prefetched record
     int row = 0, n_rows = 0;
     unsigned live_mask = 0;
     if ((p.flags & ASZ_STEP_TIC) && !(m.flags & 1u)) {
@@ -159,6 +175,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       const int spawn_cell = (p.spawn_mode == ASZ_SPAWN_REPLAY) ? p.spawn_cells[g] : -1;
       const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, p.spawn_mode, spawn_cell, p.chance_thresh, p.seed,
                                       (uint32_t)g, p.S, merged_rng ? spawn_r : nullptr);
+      ASZ_PROF(1);   // draws + tic
       if (p.rewards != nullptr && lane < 8)
         p.rewards[(size_t)g * 8 + lane] = (int8_t)(sn.reward == 1 ? 1 : sn.reward == 2 ? -1 : 0);
       if (lane == 0) {
@@ -214,15 +231,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         if (lane == 0 && n_rows > 0) { row = atomicAdd(p.row_count, n_rows); s_wtot[warp][8] += (uint32_t)n_rows; }
       }
     }
+    ASZ_PROF(2);   // results, reset, row atomic issue, record write-back
     // the next game's record streams in while this game's planes are encoded
     nxt = __shfl_sync(kFull, nxt, 0);
     if (nxt < p.G) prefetch(nxt);
+    ASZ_PROF(3);   // waiting for the work counter, issuing the prefetch
     // ---- planes of this game (rows of a game stay contiguous, ascending snake id) ----
     {
       if (n_rows > 0) {
         CellView<G> cv;
         warp_cell_view<G>(sb, sn, cv, s_lut);
         row = __shfl_sync(kFull, row, 0);
+        ASZ_PROF(4);   // cell view, waiting for the row atomic
         unsigned rest = live_mask;
         while (rest) {
           const int vs = __ffs(rest) - 1;
@@ -242,6 +262,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       }
     }
     __syncwarp();   // the board buffer is reused by the next game
+    ASZ_PROF(5);   // plane encode (ASZ_PROF 6 inside: waiting for the copy engine to release a staging buffer)
     g = nxt;
   }
   if (lane == 0) {
@@ -249,6 +270,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   }
   __syncwarp();
   if (lane < 9 && s_wtot[warp][lane] != 0u) atomicAdd(&p.totals[lane], (unsigned long long)s_wtot[warp][lane]);
+#ifdef ASZ_ENV_PROFILE
+  if (p.prof != nullptr && lane < 8) atomicAdd(&p.prof[lane], s_prof[warp][lane]);
+#endif
 }
 
 // ---- reset kernel ---------------------------------------------------------------------------------------------------
@@ -369,8 +393,8 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
   ASZ_CUDA(cudaMalloc(&e->spawn_cells, G * sizeof(int32_t)));
   ASZ_CUDA(cudaMalloc(&e->ended, G));
   ASZ_CUDA(cudaMalloc(&e->rewards, G * 8));
-  ASZ_CUDA(cudaMalloc(&e->totals, 16 * sizeof(unsigned long long)));
-  ASZ_CUDA(cudaMemset(e->totals, 0, 16 * sizeof(unsigned long long)));
+  ASZ_CUDA(cudaMalloc(&e->totals, 32 * sizeof(unsigned long long)));   // [0..15] totals, [16..23] profile build's cycle sums
+  ASZ_CUDA(cudaMemset(e->totals, 0, 32 * sizeof(unsigned long long)));
   ASZ_CUDA(cudaMemset(e->ended, 0, G));
   ASZ_CUDA(cudaMemset(e->rewards, 0, G * 8));
   ASZ_CUDA(cudaMemset(e->actions, 1, G * 8));
@@ -395,7 +419,7 @@ int asz_engine_destroy(asz_engine* e) {
 int asz_reset(asz_engine* e, void* stream) {
   if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  ASZ_CUDA(cudaMemsetAsync(e->totals, 0, 16 * sizeof(unsigned long long), st));
+  ASZ_CUDA(cudaMemsetAsync(e->totals, 0, 32 * sizeof(unsigned long long), st));
   switch (e->cfg.side) {
     case 7: return EnvLaunch<7>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
     case 11: return EnvLaunch<11>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
@@ -421,7 +445,7 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.actions = a->d_actions; p.spawn_cells = a->d_spawn_cells;
   p.planes = a->d_planes; p.row_ids = a->d_row_ids; p.keys = a->d_keys; p.max_rows = a->max_rows;
   p.row_count = a->d_row_count ? a->d_row_count : e->row_count;
-  p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals;
+  p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals; p.prof = e->totals + 16;
   p.work_counter = e->row_count + 32;
   p.hints = e->step_hints;
   ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, 64 * sizeof(int32_t), st));
@@ -489,6 +513,14 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
   if (!e || !h_totals) { set_error("null argument"); return ASZ_ERR_ARG; }
   ASZ_CUDA(cudaDeviceSynchronize());
   ASZ_CUDA(cudaMemcpy(h_totals, e->totals, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return ASZ_OK;
+}
+
+int asz_internal_profile(asz_engine* e, uint64_t* h_cycles) {
+  if (!e || !h_cycles) { set_error("null argument"); return ASZ_ERR_ARG; }
+  ASZ_CUDA(cudaDeviceSynchronize());
+  ASZ_CUDA(cudaMemcpy(h_cycles, e->totals + 16, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  ASZ_CUDA(cudaMemset(e->totals + 16, 0, 8 * sizeof(uint64_t)));
   return ASZ_OK;
 }
 

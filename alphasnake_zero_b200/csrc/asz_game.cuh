@@ -357,6 +357,9 @@ struct EncodeCtx {
   float* oth;            // the other buffer (its bulk store may still be in flight)
   const float* bg;
   uint64_t policy;       // L2 cache policy of the plane stores
+#ifdef ASZ_ENV_PROFILE
+  unsigned long long* prof_wait;
+#endif
   int prev_cur[G::CPL];  // stage index of the pixel each of this lane's cells was scattered to in `cur` (-1 none)
   int prev_oth[G::CPL];
 };
@@ -420,8 +423,14 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   const int base3 = 3 * Cc - W0 + off;          // stage index of pixel p's channel 0 = 3*A*y + 3*B*x + base3
   float* stage = ctx.cur;
   // the bulk store that read this buffer two planes ago must have finished reading it
+#ifdef ASZ_ENV_PROFILE
+  const long long prof_w0 = clock64();
+#endif
   if (lane == 0) bulk_wait_read<1>();
   __syncwarp();
+#ifdef ASZ_ENV_PROFILE
+  if (ctx.prof_wait != nullptr && lane == 0) *ctx.prof_wait += (unsigned long long)(clock64() - prof_w0);
+#endif
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
     const int s = ctx.prev_cur[q];

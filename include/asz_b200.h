@@ -127,6 +127,10 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals);
  * d_ptrs[1] = snakes (u64 [G][8]: head:16 | len:16 | health:8 | last_move:2 | alive:1 | reward:2), d_ptrs[2] = meta
  * (u32 [G][8]: game_length, episode, wall, body, head, starve, food_eaten, flags bit0 = finished).  Replaces
  * iterating `games` for liveness (mp_game_runner.py:40-42). */
+/* measurement builds only (nvcc -DASZ_ENV_PROFILE, tools/env_profile.py): per-phase cycle sums of env_step_kernel since
+ * the last call, h_cycles[8] = record wait, tic, write-back, work-counter wait + prefetch, cell view + row wait, encode,
+ * staging-buffer wait (inside encode), unused; all zero in the product build.  Synchronous. */
+int asz_internal_profile(asz_engine* e, uint64_t* h_cycles);
 int asz_internal_state(asz_engine* e, void** d_ptrs);
 /* device pointer of the engine's internal plane buffer (capacity G*S rows) and row-id buffer */
 float* asz_internal_planes(asz_engine* e);
