@@ -83,7 +83,8 @@ __device__ __forceinline__ void store_meta(uint32_t* gm, const Meta& m, int lane
 // HINTS: plane stores carry an evict_first L2 policy and the game records (read and rewritten by every launch, 21 MB at
 // 65,536 games) an evict_last one.  Worth 4 % on the device-resident path; the host-buffer path (asz_env_step_host) runs
 // 25 % SLOWER with either hint (measured, tools/env_state_probe3.py), so it uses the plain instructions.
-template <int SIDE, int WARPS, int MINB, bool HINTS>
+// ACTS: the caller supplies the actions (p.actions); false = none are read (in-kernel random actions, or no tic at all).
+template <int SIDE, int WARPS, int MINB, bool HINTS, bool ACTS>
 __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvParams p) {
   using G = Geo<SIDE>;
   using E = EncGeo<G>;
@@ -122,6 +123,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   uint32_t pf_board[BW];
   uint64_t pf_snake = 0;
   uint32_t pf_meta = 0;
+  // the caller's actions of the next game travel with its record (cp.async into a per-warp slot: no register held across
+  // the encode), instead of being an exposed load inside the tic
+  __shared__ __align__(8) uint8_t s_act[WARPS][2][8];
+  constexpr bool given_actions = ACTS;
+  int act_slot = 0;
   int g = (int)blockIdx.x * WARPS + warp;
   const uint64_t keep = HINTS ? l2_policy_evict_last() : 0ull;
   auto prefetch = [&](int gi) {
@@ -135,8 +141,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       for (int q = 0; q < BW; ++q) pf_board[q] = src[lane * BW + q];
       if (lane < 8) { pf_snake = p.snakes[(size_t)gi * 8 + lane]; pf_meta = p.meta[(size_t)gi * 8 + lane]; }
     }
+    if constexpr (given_actions) if (lane == 0) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\ncp.async.commit_group;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_act[warp][act_slot ^ 1][0])),
+                   "l"(p.actions + (size_t)gi * 8)
+                   : "memory");
+    }
   };
-  if (g < p.G) prefetch(g);
+  if (g < p.G) { prefetch(g); act_slot ^= 1; }
   while (g < p.G) {
     ASZ_PROF_DECL
     int nxt = 0;
@@ -169,8 +180,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         const uint32_t rv = (lane & 3) == 0 ? r[0] : (lane & 3) == 1 ? r[1] : (lane & 3) == 2 ? r[2] : r[3];
         move = (int)mulhi32(rv, 3u);
         spawn_r[0] = __shfl_sync(kFull, r[0], 8); spawn_r[1] = __shfl_sync(kFull, r[1], 8);
-      } else if (lane < 8) {
-        move = (int)p.actions[(size_t)g * 8 + lane];
+      } else if constexpr (given_actions) {
+        if (lane == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (lane < 8) move = (int)s_act[warp][act_slot][lane];
       }
       const int spawn_cell = (p.spawn_mode == ASZ_SPAWN_REPLAY) ? p.spawn_cells[g] : -1;
       const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, p.spawn_mode, spawn_cell, p.chance_thresh, p.seed,
@@ -263,6 +276,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
     }
     __syncwarp();   // the board buffer is reused by the next game
     ASZ_PROF(5);   // plane encode (ASZ_PROF 6 inside: waiting for the copy engine to release a staging buffer)
+    act_slot ^= 1;
     g = nxt;
   }
   if (lane == 0) {
@@ -302,15 +316,15 @@ struct EnvLaunch {
     return (size_t)(E::BGLEN + WARPS * 2 * E::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t) +
            (size_t)(G::PC + 8) * sizeof(float);
   }
-  template <int MINB, bool HINTS>
+  template <int MINB, bool HINTS, bool ACTS>
   static int launch(const EnvParams& p, cudaStream_t st) {
     static bool configured = false;
     static int n_sm = 0;
     if (!configured) {
-      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_bytes()), "cudaFuncSetAttribute(env_step_kernel)"))
         return ASZ_ERR_CUDA;
-      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
         return ASZ_ERR_CUDA;
       int dev = 0;
@@ -319,15 +333,17 @@ struct EnvLaunch {
       configured = true;
     }
     const int blocks = std::min((p.G + WARPS - 1) / WARPS, n_sm * MINB);
-    env_step_kernel<SIDE, WARPS, MINB, HINTS><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
+    env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
     return cuda_ok(cudaGetLastError(), "env_step_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
   }
   static int step(const EnvParams& p, cudaStream_t st) {
     // 3 CTAs x 8 warps per SM at 80 registers (2 x 4 at 19x19).  Measured alternatives at 11x11 (tools/env_sustain.py, us per
     // launch of 65,536 games): 8 warps x 3 CTAs 176.8 | 12 x 2 176.8 | 10 x 2 177.3 | 8 x 2 196.2 (too few warps) |
     // 7 x 4 206.6, 5 x 5 211.1, 6 x 5 227.2, 8 x 4 233 (register spills)
-    if (SIDE >= 19) return p.hints ? launch<2, true>(p, st) : launch<2, false>(p, st);
-    return p.hints ? launch<3, true>(p, st) : launch<3, false>(p, st);
+    constexpr int MINB = SIDE >= 19 ? 2 : 3;
+    const bool acts = (p.flags & ASZ_STEP_TIC) && !(p.flags & ASZ_STEP_RANDOM_ACT);
+    if (p.hints) return acts ? launch<MINB, true, true>(p, st) : launch<MINB, true, false>(p, st);
+    return acts ? launch<MINB, false, true>(p, st) : launch<MINB, false, false>(p, st);
   }
   static int reset(const GameSet& gs, int S, uint64_t seed, cudaStream_t st) {
     const int blocks = (gs.n + WARPS - 1) / WARPS;
@@ -435,6 +451,7 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   if ((a->flags & ASZ_STEP_ENCODE) && ((uintptr_t)a->d_planes & 15u)) { set_error("d_planes must be 16-byte aligned"); return ASZ_ERR_ARG; }
   if ((a->flags & ASZ_STEP_KEYS) && !a->d_keys) { set_error("ASZ_STEP_KEYS needs d_keys"); return ASZ_ERR_ARG; }
   if ((a->flags & ASZ_STEP_TIC) && !(a->flags & ASZ_STEP_RANDOM_ACT) && !a->d_actions) { set_error("d_actions is null"); return ASZ_ERR_ARG; }
+  if ((a->flags & ASZ_STEP_TIC) && !(a->flags & ASZ_STEP_RANDOM_ACT) && ((uintptr_t)a->d_actions & 7u)) { set_error("d_actions must be 8-byte aligned"); return ASZ_ERR_ARG; }
   if ((a->flags & ASZ_STEP_TIC) && a->spawn_mode == ASZ_SPAWN_REPLAY && !a->d_spawn_cells) { set_error("d_spawn_cells is null"); return ASZ_ERR_ARG; }
   if (a->spawn_mode < 0 || a->spawn_mode > 2) { set_error("bad spawn_mode"); return ASZ_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
