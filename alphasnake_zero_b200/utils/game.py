@@ -68,3 +68,61 @@ class Game:
     def get_states(self):
         """game.py:68-69: planes of the live snakes, in live-list order (encode kernel, copied to the host)."""
         return self.engine.states_of(self.id)
+
+
+# ---- replay.rep (game.py:140-141, 194-195, 281-300; read by player.py:63-79) -----------------------------------------
+# The reference draws two text frames per tic when a single game is run (mp_game_runner.py:26,52): one after the snakes
+# have moved, eaten and the food has spawned but before the dead are removed, one after.  The device tic is one launch,
+# so the first frame is rebuilt on the host from the state before the tic, the moves and the food after it.
+def _draw(width, height, food_cells, heads, bodies):
+    """heads: [(length, id, cell or None)] in live-list order; bodies: [(id, cells)] in live-list order (game.py:281-300)."""
+    board = [[0] * width for _ in range(height)]
+    for c in food_cells:
+        board[c // width][c % width] = 9
+    for _, sid, cell in sorted(heads, key=lambda h: h[0]):       # stable: ties keep the live-list order
+        if cell is not None:
+            board[cell // width][cell % width] = -(sid + 1)
+    for sid, cells in bodies:
+        for c in cells:
+            board[c // width][c % width] = sid + 1
+    return board
+
+
+def replay_frames(pre, moves, post, width, height=None):
+    """(frame before removal, frame after removal) of one tic as lists of rows.
+    pre / post: state dumps (Engine.get_state) before and after the tic; moves: relative move of every snake alive in
+    `pre`, in ascending snake id (the live-list order of game.py:87-92)."""
+    height = width if height is None else height
+    snake0, owner0, dist0 = np.asarray(pre["snake"]), np.asarray(pre["owner"]), np.asarray(pre["dist"])
+    food0 = np.asarray(pre["food"])
+    live = [i for i in range(len(snake0)) if snake0[i][0]]
+    eaten, heads, bodies = set(), [], []
+    for k, i in enumerate(live):
+        last, head, length = int(snake0[i][3]), int(snake0[i][4]), int(snake0[i][2])
+        d = (int(moves[k]) + last - 1) % 4                                   # game.py:92
+        y, x = head // width, head % width
+        y += -1 if d == 0 else 1 if d == 2 else 0                            # game.py:330-342
+        x += 1 if d == 1 else -1 if d == 3 else 0
+        cell = y * width + x if 0 <= y < height and 0 <= x < width else None
+        if cell is not None and food0[cell] and cell not in eaten:           # first come, first served (game.py:121-127)
+            eaten.add(cell)
+            length += 1
+        heads.append((length, i, cell))
+        # Snake.move pops the tail (a stamp of distance 1 leaves its cell); everything else, the old head included, is body
+        bodies.append((i, [int(c) for c in np.nonzero((owner0 == i) & (dist0 >= 2))[0]]))
+    food1 = [int(c) for c in np.nonzero(np.asarray(post["food"]))[0]]        # eaten and spawned before the first frame
+    first = _draw(width, height, food1, heads, bodies)
+    snake1, owner1 = np.asarray(post["snake"]), np.asarray(post["owner"])
+    heads, bodies = [], []
+    for i in range(len(snake1)):
+        if snake1[i][0]:
+            h = int(snake1[i][4])
+            heads.append((int(snake1[i][2]), i, h))
+            bodies.append((i, [int(c) for c in np.nonzero(owner1 == i)[0] if int(c) != h]))
+    second = _draw(width, height, food1, heads, bodies)
+    return first, second
+
+
+def frames_text(frames):
+    """the bytes Game.draw appends to replay.rep for these frames (game.py:296-300)"""
+    return "".join("".join(str(row) + "\n" for row in board) + "\n" for board in frames)

@@ -9,7 +9,7 @@ import torch
 
 from ..engine import Engine
 from .. import _lib
-from .game import Game
+from .game import Game, frames_text, replay_frames
 
 
 class GameDict(dict):
@@ -76,7 +76,12 @@ class MPGameRunner:
             actions = np.ones((self.game_cnt, 8), np.uint8)
             for (g, s), m in zip(ids, moves):
                 actions[g, s] = m
+            show = self.game_cnt == 1                      # mp_game_runner.py:26: a single game is recorded in replay.rep
+            pre = eng.get_state(0) if show else None
             eng.step(actions=torch.from_numpy(actions).to(eng.device), spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=False)
+            if show:                                       # game.py:140-141,194-195: two frames per tic
+                with open("replay.rep", "a") as f:
+                    f.write(frames_text(replay_frames(pre, [m for (g, s), m in zip(ids, moves)], eng.get_state(0), self.width)))
             ended = eng.ended.cpu().numpy()
             rw = eng.rewards.cpu().numpy()
             for g in np.nonzero(ended)[0]:

@@ -14,6 +14,7 @@ Fixtures (all numpy .npz, compressed):
   mcts_<name>.npz   reference Agent + MPGameRunner with a deterministic stub value function: recorded
                     in-tree moves, root moves, root Q, and the full (key, Q, W, N, age) tables per root turn
   funcs.npz         softermax / argmaxs / numpy.random.choice known answers
+  replay_<name>.npz the text frames Game.tic(show=True) appends to replay.rep, with the dumps they were drawn from
 """
 import hashlib
 import io
@@ -471,7 +472,50 @@ def gen_funcs():
     print("funcs: ok")
 
 
+def gen_replay(name, H, W, S, health_dec, n_games, seed, max_tics=400):
+    """Game.tic(moves, show=True) (game.py:140-141,194-195,281-300): the two text frames per tic the reference appends to
+    replay.rep, next to the pre-tic dump, the moves and the post-tic dump they were drawn from."""
+    import tempfile
+    pyrandom.seed(seed)
+    rng = np.random.default_rng(seed)
+    keys = ("snake", "owner", "dist", "food")
+    pre = {k: [] for k in keys}; post = {k: [] for k in keys}
+    t_moves, texts = [], []
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for gi in range(n_games):
+                g = rg.Game(gi, H, W, S, health_dec)
+                for t in range(max_tics):
+                    n = len(g.snakes)
+                    mv = rng.integers(0, 3, size=n).tolist()
+                    d0 = dump(g)
+                    if os.path.exists("replay.rep"):
+                        os.remove("replay.rep")
+                    res = g.tic(list(mv), True)
+                    d1 = dump(g)
+                    texts.append(open("replay.rep").read())
+                    for k in keys:
+                        pre[k].append(d0[k]); post[k].append(d1[k])
+                    t_moves.append(mv + [-1] * (S - n))
+                    if res != 0:
+                        break
+        finally:
+            os.chdir(cwd)
+    blob = "\x00".join(texts).encode()
+    out = dict(H=H, W=W, S=S, moves=np.array(t_moves, np.int8), text=np.frombuffer(blob, np.uint8))
+    for k in keys:
+        out["pre_" + k] = np.array(pre[k], np.int16); out["post_" + k] = np.array(post[k], np.int16)
+    np.savez_compressed(os.path.join(HERE, "replay_%s.npz" % name), **out)
+    print("replay_%s: %d games, %d tics" % (name, n_games, len(t_moves)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "replay":      # only the fixtures added after the first generation
+        gen_replay("11x11x4", 11, 11, 4, 1, 25, seed=21)
+        gen_replay("7x7x8", 7, 7, 8, 1, 10, seed=22)
+        sys.exit(0)
     gen_funcs()
     gen_edge_cases()
     gen_env("11x11x4", 11, 11, 4, 1, 200, seed=1)
@@ -485,3 +529,5 @@ if __name__ == "__main__":
     gen_mcts("7x7x4_dec9", 7, 7, 4, 9, G=2, base=3, training=True, D=4, breadth=8, root_turns=10, seed=13)
     gen_mcts("19x19x8", 19, 19, 8, 1, G=1, base=2, training=True, D=8, breadth=8, root_turns=3, seed=14)
     gen_mcts("11x11x4_b5", 11, 11, 4, 1, G=2, base=2, training=True, D=8, breadth=5, root_turns=4, seed=15)
+    gen_replay("11x11x4", 11, 11, 4, 1, 25, seed=21)
+    gen_replay("7x7x8", 7, 7, 8, 1, 10, seed=22)

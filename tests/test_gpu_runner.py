@@ -123,3 +123,22 @@ def test_game_view_surface():
         assert np.array_equal(st[k].view(np.uint32), og.make_state(k).view(np.uint32))
     assert len(g.snakes) == 4 and g.snakes[0].length == 3 and g.rewards == [None] * 4
     assert len(g.food) >= 2
+
+
+def test_single_game_writes_replay_rep(tmp_path, monkeypatch):
+    """test_model.py:13-23: one game with the search agent, replay.rep gets two frames per tic (game.py:140-141,194-195) in
+    the text format player.py:63-79 parses"""
+    import ast
+    from alphasnake_zero_b200.utils.agent import Agent, StubNet
+    from alphasnake_zero_b200.utils.mp_game_runner import MPGameRunner
+    monkeypatch.chdir(tmp_path)
+    gr = MPGameRunner(11, 11, 4, 9, 1, verbose=False, seed=4)
+    rewards = gr.run(Agent(StubNet(), 100, False, 4, 8))
+    assert len(rewards) == 1 and rewards[0].count(1.0) <= 1
+    pages = [p for p in open("replay.rep").read().split("\n\n") if p.strip()]
+    assert len(pages) == 2 * int(round(gr.game_length)) > 4
+    for page in pages:
+        rows = [ast.literal_eval(line) for line in page.strip().split("\n")]
+        assert len(rows) == 11 and all(len(r) == 11 and all(-4 <= v <= 9 for v in r) for r in rows)
+    first = [ast.literal_eval(line) for line in pages[0].strip().split("\n")]
+    assert sum(v < 0 for r in first for v in r) >= 1 and any(v == 9 for r in first for v in r)
