@@ -156,7 +156,10 @@ def selfplay_api_leg(rank, games, breadth, depth, turns):
     net = AlphaNNet(input_shape=(2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0, backend="native")
     alice = Agent(net, 2, True, depth, breadth)
     gr = MPGameRunner(SIDE, SIDE, SNAKES, HEALTH_DEC, games, seed=5 + rank, verbose=False)
-    gr.run(alice, max_turns=1)                       # warm-up root turn (builds the engine)
+    gr._make_engine(alice)
+    for _ in range(32):                              # games of every age, as in selfplay_leg
+        gr.engine.step(spawn_mode=2, tic=True, encode=False, auto_reset=True, random_actions=True)
+    gr.run(alice, max_turns=1)                       # warm-up root turn
     torch.cuda.synchronize()
     s0 = gr.engine.search_stats()
     n0 = len(alice.records)
@@ -169,7 +172,8 @@ def selfplay_api_leg(rank, games, breadth, depth, turns):
     return {"sims_per_sec": (s1["subgames"] - s0["subgames"]) / dt, "nn_evals_per_sec": (s1["evals"] - s0["evals"]) / dt,
             "root_turns": turns, "seconds": dt, "records": len(alice.records) - n0,
             "d2h_bytes_per_turn": rec_bytes / max(turns, 1) + games * 8 * 13, "h2d_bytes_per_turn": games * 8,
-            "api": "MPGameRunner(%d games).run(Agent(net, 2, True, %d, %d), max_turns=%d)" % (games, depth, breadth, turns)}
+            "api": "MPGameRunner(%d games).run(Agent(net, 2, True, %d, %d), max_turns=%d) after 32 uniform-random tics with in-place "
+                   "reset; host lists of ids and moves, training records copied to the host every root turn" % (games, depth, breadth, turns)}
 
 
 NET_FLOPS = {11: 1043724288, 19: 3240040448}   # per evaluation, 2 * MAC, convolutions + dense
