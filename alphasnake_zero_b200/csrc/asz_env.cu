@@ -448,7 +448,7 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   if ((a->flags & ASZ_STEP_ENCODE) && (!a->d_planes || !a->d_row_ids || !a->d_row_count || a->max_rows <= 0)) {
     set_error("ASZ_STEP_ENCODE needs d_planes, d_row_ids, d_row_count and max_rows"); return ASZ_ERR_ARG;
   }
-  if ((a->flags & ASZ_STEP_ENCODE) && ((uintptr_t)a->d_planes & 15u)) { set_error("d_planes must be 16-byte aligned"); return ASZ_ERR_ARG; }
+  if ((a->flags & ASZ_STEP_ENCODE) && ((uintptr_t)a->d_planes & (uintptr_t)(4 * kEncGran - 1))) { set_error("d_planes must be 32-byte aligned"); return ASZ_ERR_ARG; }
   if ((a->flags & ASZ_STEP_KEYS) && !a->d_keys) { set_error("ASZ_STEP_KEYS needs d_keys"); return ASZ_ERR_ARG; }
   if ((a->flags & ASZ_STEP_TIC) && !(a->flags & ASZ_STEP_RANDOM_ACT) && !a->d_actions) { set_error("d_actions is null"); return ASZ_ERR_ARG; }
   if ((a->flags & ASZ_STEP_TIC) && !(a->flags & ASZ_STEP_RANDOM_ACT) && ((uintptr_t)a->d_actions & 7u)) { set_error("d_actions must be 8-byte aligned"); return ASZ_ERR_ARG; }

@@ -344,11 +344,17 @@ __device__ __forceinline__ void warp_encode(const CellView<G>& cv, const Snake& 
 // constant buffer, the window, wall after) and later restores the touched pixels.  The staging offset `off` makes the
 // shared and global addresses agree modulo 16 bytes (planes are only 4-byte aligned: 1323 floats) and modulo the 3-float
 // pixel pattern.  Compared with v1 the warp no longer fills and copies the whole plane with LSU instructions.
+// kEncGran: every bulk copy starts and ends on a multiple of this many floats of the OUTPUT address (4 = 16 bytes, the
+// copy engine's minimum; 8 = whole 32-byte sectors, so that no L2 sector is assembled from two different copies; must be
+// <= 16 because one lane stores one edge float).  Measured per launch of 65,536 games: 4: 176.8 us, 8: 175.3 us, 32 (whole
+// lines, with an edge loop): 191.8 us.
+constexpr int kEncGran = 8;
 template <class G>
 struct EncGeo {
   static constexpr int WIN = G::SIDE * 3 * G::N;                       // floats of the window rows (693 at 11x11)
-  static constexpr int WSTAGE = ((12 + WIN + 4 + 3) / 4) * 4;          // staging floats per buffer
-  static constexpr int BGLEN = ((8 + (G::N - G::SIDE) * 3 * G::N + 4 + 3) / 4) * 4;   // per-CTA wall pattern
+  static constexpr int LEAD = kEncGran == 4 ? 12 : 24;                 // wall floats before the window (>= max staging offset)
+  static constexpr int WSTAGE = ((LEAD + WIN + kEncGran + 3) / 4) * 4; // staging floats per buffer
+  static constexpr int BGLEN = ((8 + (G::N - G::SIDE) * 3 * G::N + 2 * kEncGran + 3) / 4) * 4;   // per-CTA wall pattern
 };
 
 template <class G>
@@ -417,9 +423,11 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   else if (vrot == 2) { A = -N; B = -1; Cc = (N - SIDE + hy) * N + (N - SIDE + hx);             i0 = hy; }
   else                { A = -1; B = N;  Cc = (SIDE - 1 - hx) * N + (N - SIDE + hy);             i0 = SIDE - 1 - hx; }
   const int W0 = i0 * 3 * N, W1 = W0 + E::WIN;
-  const int a0 = (int)(gidx0 & 3);              // misalignment of the plane's first float
-  const int a = (a0 + W0) & 3;
-  const int off = (9 * a) % 12;                 // off % 4 == a, off % 3 == 0
+  constexpr int GR = kEncGran;
+  const int a0 = (int)(gidx0 & (GR - 1));       // misalignment of the plane's first float, in floats past a GR boundary
+  const int a = (a0 + W0) & (GR - 1);           // same for the window's first float
+  int off = (9 * (a & 3)) % 12;                 // staging offset of the window: off % 4 == a % 4 (shared and global
+  while (GR > 4 && off < a) off += 12;          // addresses agree modulo 16 bytes), off % 3 == 0 (pixel phase), off >= a
   const int base3 = 3 * Cc - W0 + off;          // stage index of pixel p's channel 0 = 3*A*y + 3*B*x + base3
   float* stage = ctx.cur;
   // the bulk store that read this buffer two planes ago must have finished reading it
@@ -465,10 +473,10 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   if (out == nullptr) return;
   fence_proxy_async_smem();
   __syncwarp();
-  // plane-relative element ranges (32-bit): [eA, eE) is the 16-byte aligned interior of the plane, [EA, EE) the aligned
-  // cover of the window clipped to it
-  const int eA = (4 - a0) & 3, eE = PLANE - ((a0 + PLANE) & 3);
-  int EA = W0 - a, EE = W1 + ((4 - ((a0 + W1) & 3)) & 3);
+  // plane-relative element ranges (32-bit): [eA, eE) is the GR-aligned interior of the plane, [EA, EE) the aligned cover of
+  // the window clipped to it
+  const int eA = (GR - a0) & (GR - 1), eE = PLANE - ((a0 + PLANE) & (GR - 1));
+  int EA = W0 - a, EE = W1 + ((GR - ((a0 + W1) & (GR - 1))) & (GR - 1));
   if (EA < eA) EA = eA;
   if (EE > eE) EE = eE;
   float* obase = out + gidx0;
@@ -477,17 +485,14 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
     bulk_s2g<kHint>(obase + EA, stage + (EA - W0 + off), (uint32_t)((EE - EA) * 4), ctx.policy);                       // the window rows
     if (eE > EE) bulk_s2g<kHint>(obase + EE, ctx.bg + 4 * (EE % 3), (uint32_t)((eE - EE) * 4), ctx.policy);            // wall after the window
     bulk_commit();
-  } else if (lane <= 6) {
-    // up to 3 floats before the first and after the last 16-byte boundary of the plane
-    const int k = lane - 1;                                                                          // 0..2 head, 3..5 tail
-    const bool is_head = k < 3;
-    const int e = is_head ? k : eE + (k - 3);
+  }
+  if (lane >= 1 && lane <= 2 * (GR - 1)) {
+    // up to GR - 1 floats before the first and after the last GR boundary of the plane
+    const int k = lane - 1;                                                                          // head: 0..GR-2, tail: GR-1..
+    const bool is_head = k < GR - 1;
+    const int e = is_head ? k : eE + (k - (GR - 1));
     const bool on = is_head ? (k < eA) : (e < PLANE);
-    if (on) {
-      // PLANE % 3 == 0 and eE = PLANE - (0..3): the phase of a tail element follows from its distance to the end
-      const int ph = is_head ? k : (3 - (PLANE - e)) % 3;
-      obase[e] = (e >= W0 && e < W1) ? stage[e - W0 + off] : ((ph == 1) ? 1.0f : 0.0f);
-    }
+    if (on) obase[e] = (e >= W0 && e < W1) ? stage[e - W0 + off] : ((e % 3 == 1) ? 1.0f : 0.0f);      // PLANE % 3 == 0
   }
   ctx.cur = ctx.oth; ctx.oth = stage;
 #pragma unroll

@@ -97,7 +97,7 @@ typedef struct {
   int32_t spawn_mode;
   const uint8_t* d_actions;      /* [G*8] relative move per (game, snake id); read where the snake is alive */
   const int32_t* d_spawn_cells;  /* [G] for ASZ_SPAWN_REPLAY */
-  float* d_planes;               /* [max_rows][2*side-1][2*side-1][3] float32 NHWC, rows compacted; 16-byte aligned */
+  float* d_planes;               /* [max_rows][2*side-1][2*side-1][3] float32 NHWC, rows compacted; 32-byte aligned */
   int32_t* d_row_ids;            /* [max_rows] game*8 + snake of every row written */
   uint64_t* d_keys;              /* [max_rows*2] when ASZ_STEP_KEYS */
   int32_t max_rows;

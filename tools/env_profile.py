@@ -6,6 +6,14 @@ warp-cycles per phase for: A device path, B encode only, C device path after B.
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROF_LIB = os.path.join(ROOT, "tools", "libasz_b200_prof.so")
+if len(sys.argv) > 2 and sys.argv[1] == "build-variant":       # python tools/env_profile.py build-variant NAME -DFLAG ...
+    csrc = os.path.join(ROOT, "alphasnake_zero_b200", "csrc")
+    out = os.path.join(ROOT, "tools", "libasz_b200_%s.so" % sys.argv[2])
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+                           "--expt-relaxed-constexpr"] + sys.argv[3:] + ["-shared", "-o", out] +
+                          [os.path.join(csrc, f) for f in ("asz_env.cu", "asz_mcts.cu", "asz_net.cu")] + ["-lcuda"])
+    print(out)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     csrc = os.path.join(ROOT, "alphasnake_zero_b200", "csrc")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
