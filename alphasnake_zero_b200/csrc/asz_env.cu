@@ -378,18 +378,8 @@ extern "C" {
 const char* asz_last_error(void) { return g_err.c_str(); }
 int asz_version(void) { return ASZ_VERSION; }
 
-int asz_engine_create(asz_engine** out, const asz_config* cfg) {
-  if (!out || !cfg) { set_error("asz_engine_create: null argument"); return ASZ_ERR_ARG; }
-  if (cfg->side != 7 && cfg->side != 11 && cfg->side != 19) { set_error("side must be 7, 11 or 19"); return ASZ_ERR_ARG; }
-  if (cfg->snakes < 1 || cfg->snakes > ASZ_MAX_SNAKES) { set_error("snakes must be in 1..8"); return ASZ_ERR_ARG; }
-  if (cfg->games < 1) { set_error("games must be >= 1"); return ASZ_ERR_ARG; }
-  if (cfg->health_dec < 0 || cfg->health_dec > 100) { set_error("health_dec out of range"); return ASZ_ERR_ARG; }
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    set_error("no CUDA device: this engine has no CPU fallback");
-    return ASZ_ERR_CUDA;
-  }
-  asz_engine* e = new asz_engine();
+// allocations of asz_engine_create; on failure the caller destroys the partially built engine (cudaFree(nullptr) is a no-op)
+static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   e->cfg = *cfg;
   { const char* v = getenv("ASZ_ENV_HINTS"); e->device_hints = v ? atoi(v) : 1; }            // experiments only
   { const char* v = getenv("ASZ_ENV_HINTS_HOST"); e->host_hints = v ? atoi(v) : 0; }
@@ -401,7 +391,7 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
   e->chance_thresh = th <= 0.0 ? 0u : th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
   const size_t G = (size_t)cfg->games, rows = G * (size_t)cfg->snakes;
   int rc = gameset_alloc(e->root, cfg->games, e->pc);
-  if (rc != ASZ_OK) { delete e; return rc; }
+  if (rc != ASZ_OK) return rc;
   ASZ_CUDA(cudaMalloc(&e->planes, rows * (size_t)e->plane * sizeof(float) + 16));
   ASZ_CUDA(cudaMalloc(&e->row_ids, rows * sizeof(int32_t)));
   ASZ_CUDA(cudaMalloc(&e->row_count, 64 * sizeof(int32_t)));  // [0] rows of the last step, [32] work counter (own 128-byte line)
@@ -416,8 +406,26 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
   ASZ_CUDA(cudaMemset(e->actions, 1, G * 8));
   if (cfg->max_breadth > 0) {
     rc = search_create(e);
-    if (rc != ASZ_OK) { asz_engine_destroy(e); return rc; }
+    if (rc != ASZ_OK) return rc;
   }
+  return ASZ_OK;
+}
+
+
+int asz_engine_create(asz_engine** out, const asz_config* cfg) {
+  if (!out || !cfg) { set_error("asz_engine_create: null argument"); return ASZ_ERR_ARG; }
+  if (cfg->side != 7 && cfg->side != 11 && cfg->side != 19) { set_error("side must be 7, 11 or 19"); return ASZ_ERR_ARG; }
+  if (cfg->snakes < 1 || cfg->snakes > ASZ_MAX_SNAKES) { set_error("snakes must be in 1..8"); return ASZ_ERR_ARG; }
+  if (cfg->games < 1) { set_error("games must be >= 1"); return ASZ_ERR_ARG; }
+  if (cfg->health_dec < 0 || cfg->health_dec > 100) { set_error("health_dec out of range"); return ASZ_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this engine has no CPU fallback");
+    return ASZ_ERR_CUDA;
+  }
+  asz_engine* e = new asz_engine();
+  const int rc = engine_alloc(e, cfg);
+  if (rc != ASZ_OK) { asz_engine_destroy(e); return rc; }
   *out = e;
   return ASZ_OK;
 }

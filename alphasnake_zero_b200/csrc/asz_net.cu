@@ -760,14 +760,11 @@ static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, fl
 
 extern "C" {
 
-int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images) {
-  if (!out || !w) { set_error("null argument"); return ASZ_ERR_ARG; }
-  if (w->side != 7 && w->side != 11 && w->side != 19) { set_error("side must be 7, 11 or 19"); return ASZ_ERR_ARG; }
-  if (chunk_images < 1) { set_error("chunk_images must be >= 1"); return ASZ_ERR_ARG; }
-  asz_net* n = new asz_net();
+// allocations of asz_net_create; on failure the caller destroys the partially built object (cudaFree(nullptr) is a no-op)
+static int net_alloc(asz_net* n, const asz_net_weights* w, int32_t chunk_images) {
   n->w = *w;
   n->side = w->side; n->real = 2 * w->side - 1; n->pitch = pitch_of(w->side); n->img_stride = n->pitch * img_rows_of(w->side);
-  if (n->pitch + 1 > kHalo) { set_error("board too large for the halo of conv_tile_kernel"); delete n; return ASZ_ERR_ARG; }
+  if (n->pitch + 1 > kHalo) { set_error("board too large for the halo of conv_tile_kernel"); return ASZ_ERR_ARG; }
   n->chunk = chunk_images;
   const size_t P = (size_t)chunk_images * n->img_stride;
   const size_t P_pad = (P + 511) / 512 * 512;                 // whole pair super-tiles
@@ -790,7 +787,7 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
     const char* v = getenv("ASZ_NET_VARIANT");
     if (v && v[0] >= '1' && v[0] <= '3') n->variant = v[0] - '0';
   }
-  { int rc = configure_umma_kernels(); if (rc != ASZ_OK) { delete n; return rc; } }
+  { int rc = configure_umma_kernels(); if (rc != ASZ_OK) return rc; }
   ASZ_CUDA(cudaFuncSetAttribute(dense_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   ASZ_CUDA(cudaMalloc(&n->w1r, (size_t)n->img_stride * 128 * sizeof(float)));
   dense1_raster_kernel<<<(n->img_stride * 128 + 255) / 256, 256>>>(w->dense1_w, n->real, n->pitch, n->img_stride, n->w1r);
@@ -803,6 +800,17 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
     ASZ_CUDA(cudaGetLastError());
   }
   ASZ_CUDA(cudaDeviceSynchronize());
+  return ASZ_OK;
+}
+
+
+int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images) {
+  if (!out || !w) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if (w->side != 7 && w->side != 11 && w->side != 19) { set_error("side must be 7, 11 or 19"); return ASZ_ERR_ARG; }
+  if (chunk_images < 1) { set_error("chunk_images must be >= 1"); return ASZ_ERR_ARG; }
+  asz_net* n = new asz_net();
+  const int rc = net_alloc(n, w, chunk_images);
+  if (rc != ASZ_OK) { asz_net_destroy(n); return rc; }
   *out = n;
   return ASZ_OK;
 }

@@ -413,7 +413,11 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- reduce over ranks: max time, sum of work ----------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local)], dtype=torch.float64, device=dev)
+    rank_ms = None
     if world > 1:
+        allv = [torch.zeros_like(vals) for _ in range(world)]
+        dist.all_gather(allv, vals)
+        rank_ms = {"device_resident": [round(float(v[0]) / K, 5) for v in allv], "e2e": [round(float(v[1]) / K, 5) for v in allv]}
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(mx[0]), float(mx[1])
@@ -455,6 +459,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": K, "clocks": clocks,
     }
     out.update(sp)
+    if rank_ms is not None:   # ms per step of every rank: the aggregate above is paced by the slowest one
+        out["rank_ms_per_step"] = rank_ms
     if bcast is not None:
         out["weight_broadcast"] = bcast
     if world == 1 and not args.no_cpu_baseline:
