@@ -91,11 +91,22 @@ def test_search_replay_against_reference(name):
     (11, 2, 40, 6, 8, 10.0, True, 12), (11, 4, 768, 8, 32, 2.0, True, 2)])
 def test_native_search_against_oracle(side, S, G, D, breadth, base, training, turns):
     """The GPU samples with its own RNG and records the trace; the oracle replays it."""
+    _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, 20)
+
+
+def test_native_search_across_table_compactions():
+    """a table of 2^12 slots: the live entries are compacted into a fresh table several times during the run (more than
+    half of the slots taken, many of them by evicted entries, agent.py:101-110); keys, visit counts, W and ages still match"""
+    n = _native_search_against_oracle(11, 4, 32, 4, 16, 2.0, True, 12, 12)
+    assert n >= 2, "the run did not compact the table (%d times)" % n
+
+
+def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, table_log2):
     import torch
     from oracle import oracle as orc
     seed = 77
     eng = _engine(side=side, snakes=S, health_dec=1, games=G, seed=seed, max_depth=D, max_breadth=breadth,
-                  softmax_base=base, training=training, table_log2=20)
+                  softmax_base=base, training=training, table_log2=table_log2)
     eng.reset()
     info = eng.search_info()
     games = []
@@ -103,6 +114,7 @@ def test_native_search_against_oracle(side, S, G, D, breadth, base, training, tu
         g = orc.OracleGame(side, side, S, 1); g.init_native(seed, gi, 0); g.set_ids(gi, 0); games.append(g)
     agent = orc.OracleAgent(base=base, training=training, max_depth=D, max_breadth=breadth)
     done = [False] * G
+    compactions, last_occupied, last_inserts = 0, 0, 0
     for t in range(turns):
         tree = torch.full((info["epochs"], info["max_steps"], G * info["P"], S), 255, dtype=torch.uint8, device="cuda")
         q, mv = eng.search(value_fn=None, trace=tree, trace_mode=2)
@@ -129,6 +141,9 @@ def test_native_search_against_oracle(side, S, G, D, breadth, base, training, tu
         assert st["evals"] == agent.stat("evals") and st["node_visits"] == agent.stat("node_visits")
         assert st["subgame_tics"] == agent.stat("subgame_tics") and st["subgames"] == agent.stat("subgames")
         assert st["collisions"] == 0 and st["overflow"] == 0 and agent.stat("alias_errors") == 0
+        if st["occupied"] - last_occupied < st["inserts"] - last_inserts:
+            compactions += 1            # slots were given back: the table was rebuilt from its live entries
+        last_occupied, last_inserts = st["occupied"], st["inserts"]
         # root tic on both sides (native spawn) with the GPU's root moves
         actions = np.ones((G, 8), np.uint8)
         for (g_i, s), m in zip(ids, root_moves):
@@ -145,6 +160,7 @@ def test_native_search_against_oracle(side, S, G, D, breadth, base, training, tu
         for g_i in range(0, G, 5):
             assert_dump_equal(eng.get_state(g_i), games[g_i].dump(), "root game %d after turn %d" % (g_i, t))
     eng.close()
+    return compactions
 
 
 def test_policy_functions_against_reference():
