@@ -222,7 +222,8 @@ typedef struct asz_net asz_net;
 int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images);
 int asz_net_destroy(asz_net* net);
 /* convolution kernel variant: 1 = one tile per CTA, 2 = persistent single-CTA, 3 = persistent CTA pairs (cta_group::2).
- * All three compute the same bits; the default is the fastest (environment override: ASZ_NET_VARIANT). */
+ * 2 and 3 compute the same bits (same accumulation order), 1 agrees to bf16 rounding; the default is 3, the fastest
+ * (environment override: ASZ_NET_VARIANT). */
 int asz_net_set_variant(asz_net* net, int32_t variant);
 /* d_planes [count][2*side-1][2*side-1][3] float32 NHWC -> d_values [count][3] float32 tanh outputs (no obstacle mask;
  * asz_obstacle_mask applies AlphaNNet.v's mask).  bf16 operands, fp32 accumulation. */
