@@ -473,17 +473,23 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.flags = a->flags; p.spawn_mode = a->spawn_mode; p.chance_thresh = e->chance_thresh; p.seed = e->cfg.seed;
   p.actions = a->d_actions; p.spawn_cells = a->d_spawn_cells;
   p.planes = a->d_planes; p.row_ids = a->d_row_ids; p.keys = a->d_keys; p.max_rows = a->max_rows;
-  p.row_count = a->d_row_count ? a->d_row_count : e->row_count;
+  // rows are always counted in the engine's own counter (its L2 slice is known not to be the work counter's; a caller's
+  // 4-byte buffer could land anywhere) and copied to the caller's d_row_count after the launch
+  p.row_count = e->row_count;
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals; p.prof = e->totals + 16;
   p.work_counter = e->row_count + kWorkCounterAt;
   p.hints = e->step_hints;
   ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, (kWorkCounterAt + 32) * sizeof(int32_t), st));
-  if (p.row_count != e->row_count) ASZ_CUDA(cudaMemsetAsync(p.row_count, 0, sizeof(int32_t), st));
+  int rc;
   switch (e->cfg.side) {
-    case 7: return EnvLaunch<7>::step(p, st);
-    case 11: return EnvLaunch<11>::step(p, st);
-    default: return EnvLaunch<19>::step(p, st);
+    case 7: rc = EnvLaunch<7>::step(p, st); break;
+    case 11: rc = EnvLaunch<11>::step(p, st); break;
+    default: rc = EnvLaunch<19>::step(p, st); break;
   }
+  if (rc != ASZ_OK) return rc;
+  if (a->d_row_count && a->d_row_count != e->row_count)
+    ASZ_CUDA(cudaMemcpyAsync(a->d_row_count, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return ASZ_OK;
 }
 
 int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
