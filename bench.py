@@ -77,6 +77,22 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def sample_now(self):
+        """one sample taken by the caller's thread (the launches of the timed region are queued and still executing)"""
+        if self.nvml is None:
+            return
+        n = self.nvml
+        try:
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = get_reasons(self.handle)
+            pre = "nvmlClocksEventReason" if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else "nvmlClocksThrottleReason"
+            bits = [getattr(n, pre + k) for k in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap")]
+            self.rows.append([str(sm), str(mx), "0"] + ["Active" if mask & b else "Not Active" for b in bits])
+        except Exception:
+            pass
+
     def _poll(self):
         n = self.nvml
         bits = [(n.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (n.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
@@ -329,6 +345,8 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(K):
         eng.step(**kw)
     ev1.record()
+    if rank == 0:
+        sampler.sample_now()      # the K launches are queued and executing: a sample from this thread is inside the region
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
