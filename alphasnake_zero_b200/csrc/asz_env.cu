@@ -390,7 +390,8 @@ static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   e->pc = pc_of(cfg->side);
   e->plane = (2 * cfg->side - 1) * (2 * cfg->side - 1) * 3;
   double th = (double)cfg->food_chance * 4294967296.0;
-  e->chance_thresh = th <= 0.0 ? 0u : th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
+  // 0 = the reference's `food_spawn_chance > 0.0` guard is false (game.py:130): no spawning at all, not even on a board without food
+  e->chance_thresh = cfg->food_chance <= 0.0f ? 0u : th >= 4294967295.0 ? 4294967295u : th < 1.0 ? 1u : (uint32_t)th;
   const size_t G = (size_t)cfg->games, rows = G * (size_t)cfg->snakes;
   int rc = gameset_alloc(e->root, cfg->games, e->pc);
   if (rc != ASZ_OK) return rc;
@@ -588,7 +589,7 @@ static int gs_get_state(const asz_config& cfg, int pc, const GameSet& gs, int32_
     const uint64_t v = sn[s];
     int32_t* o = h_snake + 6 * s;
     const int head = (int)(v & 0xFFFF), rw = (int)((v >> 43) & 3);
-    o[0] = (int)((v >> 42) & 1); o[1] = (int)((v >> 32) & 0xFF); o[2] = (int)((v >> 16) & 0xFFFF);
+    o[0] = (int)((v >> 42) & 1); o[1] = (int)(int16_t)(uint16_t)(((v >> 32) & 0xFF) | (((v >> 48) & 0xFF) << 8)); o[2] = (int)((v >> 16) & 0xFFFF);
     o[3] = (int)((v >> 40) & 3); o[4] = head == 0xFFFF ? -1 : head; o[5] = rw == 1 ? 1 : rw == 2 ? -1 : 0;
   }
   for (int k = 0; k < 5; ++k) h_counters[k] = (int32_t)meta[2 + k];
@@ -618,8 +619,10 @@ static int gs_set_state(const asz_config& cfg, int pc, GameSet& gs, int32_t game
       live += alive;
       const int head = (alive && o[4] >= 0) ? o[4] : 0xFFFF;
       const int rw = o[5] > 0 ? 1 : o[5] < 0 ? 2 : 0;
-      v = (uint64_t)(head & 0xFFFF) | ((uint64_t)((alive ? o[2] : 0) & 0xFFFF) << 16) | ((uint64_t)((alive ? o[1] : 0) & 0xFF) << 32) |
-          ((uint64_t)(o[3] & 3) << 40) | ((uint64_t)alive << 42) | ((uint64_t)rw << 43);
+      const int hp = alive ? o[1] : 0;
+      if (hp < -32768 || hp > 32767) { set_error("health out of range"); return ASZ_ERR_ARG; }
+      v = (uint64_t)(head & 0xFFFF) | ((uint64_t)((alive ? o[2] : 0) & 0xFFFF) << 16) | ((uint64_t)(hp & 0xFF) << 32) |
+          ((uint64_t)(o[3] & 3) << 40) | ((uint64_t)alive << 42) | ((uint64_t)rw << 43) | ((uint64_t)((hp >> 8) & 0xFF) << 48);
     }
     sn[s] = v;
   }

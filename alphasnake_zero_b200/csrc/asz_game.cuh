@@ -23,7 +23,10 @@ struct Geo {
 };
 
 // ---- packed records in HBM ---------------------------------------------------------------------------------------
-// snake: head:16 | len:16 | health:8 | last_move:2 | alive:1 | reward:2 (0 none, 1 = +1, 2 = -1)
+// snake: head:16 | len:16 | health low byte:8 | last_move:2 | alive:1 | reward:2 (0 none, 1 = +1, 2 = -1) | pad:3 |
+// health high byte:8.  Health is a SIGNED 16-bit value split over bits 32..39 and 48..55: the kill chain of game.py:156-165
+// is an elif chain, so the winner of a head-on collision skips the starvation check and can end a tic alive with
+// health <= 0 (down to 1 - 7*health_dec after seven wins in a row); it starves on the next tic it does not eat.
 struct Snake {
   int head;    // cell index, 0xFFFF = none
   int len;
@@ -34,11 +37,12 @@ struct Snake {
 };
 __device__ __forceinline__ uint64_t pack_snake(const Snake& s) {
   return (uint64_t)(s.head & 0xFFFF) | ((uint64_t)(s.len & 0xFFFF) << 16) | ((uint64_t)(s.health & 0xFF) << 32) |
-         ((uint64_t)(s.last & 3) << 40) | ((uint64_t)(s.alive & 1) << 42) | ((uint64_t)(s.reward & 3) << 43);
+         ((uint64_t)(s.last & 3) << 40) | ((uint64_t)(s.alive & 1) << 42) | ((uint64_t)(s.reward & 3) << 43) |
+         ((uint64_t)((s.health >> 8) & 0xFF) << 48);
 }
 __device__ __forceinline__ Snake unpack_snake(uint64_t v) {
   Snake s;
-  s.head = (int)(v & 0xFFFF); s.len = (int)((v >> 16) & 0xFFFF); s.health = (int)((v >> 32) & 0xFF);
+  s.head = (int)(v & 0xFFFF); s.len = (int)((v >> 16) & 0xFFFF); s.health = (int)(int16_t)(uint16_t)(((v >> 32) & 0xFF) | (((v >> 48) & 0xFF) << 8));
   s.last = (int)((v >> 40) & 3); s.alive = (int)((v >> 42) & 1); s.reward = (int)((v >> 43) & 3);
   return s;
 }
@@ -103,7 +107,7 @@ __device__ __forceinline__ void warp_init_native(uint16_t* sb, Snake& sn, Meta& 
 
 // ---- Game.tic (game.py:87-205) -----------------------------------------------------------------------------------
 // move: this lane's relative move (0 left, 1 straight, 2 right), read only where sn.alive.
-// spawn_mode 0: none (sub-games, game.py:268), 1: replay (spawn_cell or -1), 2: native Philox.
+// spawn_mode 0: none (sub-games, game.py:268), 1: replay (spawn_cell or -1), 2: native Philox (never when chance_thresh == 0).
 template <class G>
 // spawn_r (optional): the two RS_SPAWN draws of this tic when the caller already has them (the env kernel computes them
 // in the same SIMT pass as the random actions); nullptr = drawn here.
@@ -167,7 +171,7 @@ __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, 
   if (spawn_mode == 1) {
     if (lane == 0 && spawn_cell >= 0) sb[spawn_cell] = kFood;
     __syncwarp();
-  } else if (spawn_mode == 2) {
+  } else if (spawn_mode == 2 && chance_thresh != 0u) {   // game.py:130 `if self.food_spawn_chance > 0.0` (threshold 0 = chance 0)
     uint32_t r[4];
     if (spawn_r != nullptr) { r[0] = spawn_r[0]; r[1] = spawn_r[1]; }
     else philox4x32_10(game_id, m.episode, RS_SPAWN, m.turn, seed, r);

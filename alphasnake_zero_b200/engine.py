@@ -80,12 +80,13 @@ class Engine:
         check(self.L.asz_get_state(self.h, game, _np(snake), _np(owner), _np(dist), _np(food), _np(counters)))
         return dict(snake=snake, owner=owner, dist=dist, food=food, counters=counters)
 
-    def set_state(self, game, d):
+    def set_state(self, game, d, episode=0):
+        """d: canonical dump (asz_get_state); `episode` is the episode counter of the game's RNG streams (0 for a fresh game)."""
         a = {k: np.ascontiguousarray(d[k], dtype=np.int32) for k in ("snake", "owner", "dist", "food")}
         cnt = np.zeros(8, np.int32)
         c = np.asarray(d["counters"]).astype(np.int32)
         cnt[:6] = c[:6]
-        cnt[6] = 0
+        cnt[6] = episode
         cnt[7] = 0
         check(self.L.asz_set_state(self.h, game, _np(a["snake"]), _np(a["owner"]), _np(a["dist"]), _np(a["food"]), _np(cnt)))
 

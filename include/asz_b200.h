@@ -124,7 +124,8 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
 int asz_get_totals(asz_engine* e, uint64_t* h_totals);
 
 /* device pointers of the packed root-game records, read-only for callers: d_ptrs[0] = cells (u16 [G][padded cells]),
- * d_ptrs[1] = snakes (u64 [G][8]: head:16 | len:16 | health:8 | last_move:2 | alive:1 | reward:2), d_ptrs[2] = meta
+ * d_ptrs[1] = snakes (u64 [G][8]: head:16 | len:16 | health low byte:8 | last_move:2 | alive:1 | reward:2 | pad:3 |
+ * health high byte:8; health is a signed 16-bit value, it can be <= 0 for a head-on winner, game.py:156-165), d_ptrs[2] = meta
  * (u32 [G][8]: game_length, episode, wall, body, head, starve, food_eaten, flags bit0 = finished).  Replaces
  * iterating `games` for liveness (mp_game_runner.py:40-42). */
 /* measurement builds only (nvcc -DASZ_ENV_PROFILE, tools/env_profile.py): per-phase cycle sums of env_step_kernel since

@@ -209,7 +209,7 @@ int og_tic(ogame *g, const int *moves, int spawn_mode, int spawn_cell, uint32_t 
         if (occ[spawn_cell]) fprintf(stderr, "og_tic: replayed food cell %d is not empty\n", spawn_cell);
         g->food[spawn_cell] = 1;
       }
-    } else {
+    } else if (chance_thresh != 0u) {   /* game.py:130 `if self.food_spawn_chance > 0.0`: threshold 0 = chance 0 = never */
       uint32_t r[4];
       og_philox(g->game_id, g->episode, RS_SPAWN, (uint32_t)g->game_length, seed, r);
       if (n_food == 0 || r[0] <= chance_thresh) {

@@ -82,7 +82,9 @@ def _p(a):
 
 def chance_threshold(chance):
     """u32 threshold of the engine's spawn coin: spawn iff philox_u32 <= threshold (game.py:131 `random() <= chance`)."""
-    return int(min(max(int(chance * 4294967296.0), 0), 4294967295))
+    if chance <= 0.0:
+        return 0                                   # game.py:130: a chance of 0 disables spawning altogether
+    return int(min(max(int(chance * 4294967296.0), 1), 4294967295))
 
 
 class OracleGame:

@@ -11,6 +11,8 @@ Fixtures (all numpy .npz, compressed):
   env_<name>.npz    random-play games: initial layouts, per-tic moves / spawn cell / post-tic canonical
                     dump / blake2b-64 digest of every live snake's plane, plus full planes of a few tics
   edge_cases.npz    hand-built single-tic scenarios for every trap of SURVEY.md Appendix D
+  edge_sequences.npz hand-built MULTI-tic scenarios: a head-on winner that ends a tic alive with health <= 0
+                    (game.py:156-165 is an elif chain) at health_dec 9 / 3 / 1, then starves, eats, or wins again
   mcts_<name>.npz   reference Agent + MPGameRunner with a deterministic stub value function: recorded
                     in-tree moves, root moves, root Q, and the full (key, Q, W, N, age) tables per root turn
   funcs.npz         softermax / argmaxs / numpy.random.choice known answers
@@ -282,6 +284,85 @@ def gen_edge_cases():
 
 
 # ---------------------------------------------------------------------------------------------
+def gen_edge_sequences():
+    """Multi-tic scenarios (11x11, 4 snake slots, no food spawn).  game.py:156-165 is an elif chain: a snake that shares its
+    head cell with a shorter snake takes the head-on branch and skips the starvation check, so it can end a tic alive with
+    health <= 0; the next tic it starves (game.py:163-165) unless it eats (health = 100, game.py:123-125) or wins again."""
+    H = W = 11
+    S = 4
+    cases = []
+
+    def add(name, snakes, last_moves, food, move_seq, health_dec):
+        g = build_ref_game(H, W, S, health_dec, snakes, last_moves, food, chance=0.0)
+        before = dump(g)
+        tics = []
+        min_health = 1000
+        for moves in move_seq:
+            n = len(g.snakes)
+            assert len(moves) == n, (name, moves, n)
+            res = g.tic(list(moves))
+            after = dump(g)
+            planes = [np.ascontiguousarray(p) for p in g.get_states()] if res == 0 else []   # ended games emit no rows
+            for sn in g.snakes:
+                min_health = min(min_health, sn.health)
+            tics.append(dict(moves=list(moves), after=after, ended=0 if res == 0 else 1, planes=planes))
+            if res != 0:
+                break
+        assert len(tics) == len(move_seq), name
+        cases.append(dict(name=name, before=before, tics=tics, health_dec=health_dec, min_health=min_health))
+
+    far = (100, [(9, 6), (9, 5), (9, 4)])          # bystanders that keep the game going for three tics, heading right / left
+    far2 = (100, [(7, 4), (7, 5), (7, 6)])
+    A4 = [(5, 4), (5, 3), (5, 2), (5, 1)]          # length 4 heading right; meets B3 on (5, 5)
+    B3 = [(5, 6), (5, 7), (5, 8)]                  # length 3 heading left
+    food_far = (1, 9)                              # a food cell so that the food channel shows (101 - health) * 0.01
+    for dec, hp in ((9, 5), (9, 9), (3, 2), (3, 3), (1, 1)):
+        tag = "dec%d_hp%d" % (dec, hp)
+        # wins the head-on with health hp - dec <= 0, then goes straight without eating: starves on the second tic
+        add("neg_health_starves_" + tag, [(hp, A4), (100, B3), far, far2], [1, 3, 1, 3], [food_far],
+            [[1, 1, 1, 1], [1, 1, 1], [1, 1]], dec)
+        # ... turns onto food on the second tic: back to 100 and grows
+        add("neg_health_eats_" + tag, [(hp, A4), (100, B3), far, far2], [1, 3, 1, 3], [food_far, (4, 5)],
+            [[1, 1, 1, 1], [0, 1, 1], [1, 1, 1]], dec)
+        # ... runs into the wall on the second tic: wall has priority over starvation (one cause, game.py:148-165)
+        add("neg_health_wall_" + tag, [(hp, [(0, 4), (0, 3), (0, 2), (0, 1)]), (100, [(0, 6), (0, 7), (0, 8)]), far, far2],
+            [1, 3, 1, 3], [food_far], [[1, 1, 1, 1], [0, 1, 1]], dec)
+    # two head-on wins in a row: 5 > 3 on (5, 5), then 5 > 4 on (5, 6); health falls twice below zero, then starvation
+    A5 = [(5, 4), (5, 3), (5, 2), (5, 1), (5, 0)]
+    C4 = [(3, 6), (2, 6), (1, 6), (0, 6)]          # heading down: (4, 6) after one tic, (5, 6) after two
+    add("neg_health_twice_dec9", [(5, A5), (100, B3), (100, C4), far2], [1, 3, 2, 3], [food_far],
+        [[1, 1, 1, 1], [1, 1, 1], [1, 1]], 9)
+    add("neg_health_twice_dec1", [(1, A5), (100, B3), (100, C4), far2], [1, 3, 2, 3], [food_far],
+        [[1, 1, 1, 1], [1, 1, 1], [1, 1]], 1)
+    # the head-on winner with negative health is the last snake standing: reward +1 with health <= 0
+    add("neg_health_wins_game_dec9", [(5, A4), (100, B3), None, None], [1, 3, 0, 0], [food_far], [[1, 1]], 9)
+    # health exactly 0 after a head-on win (dec 3, health 3); starves on the next tic
+    add("zero_health_then_starves_dec3", [(3, A4), (100, B3), far, None], [1, 3, 1, 0], [], [[1, 1, 1], [0, 1]], 3)
+    assert min(c["min_health"] for c in cases) < 0 and any(c["min_health"] == 0 for c in cases)
+    out = dict(names=np.array([c["name"] for c in cases]), health_dec=np.array([c["health_dec"] for c in cases], np.int32),
+               min_health=np.array([c["min_health"] for c in cases], np.int32))
+    for k in ("snake", "owner", "dist", "food", "counters"):
+        out["before_" + k] = np.array([c["before"][k] for c in cases], np.int32)
+    tic_ptr, mv, ended, planes, pl_ptr = [0], [], [], [], [0]
+    after = {k: [] for k in ("snake", "owner", "dist", "food", "counters")}
+    for c in cases:
+        for t in c["tics"]:
+            mv.append(t["moves"] + [-1] * (S - len(t["moves"])))
+            ended.append(t["ended"])
+            for k in after:
+                after[k].append(t["after"][k])
+            planes += t["planes"]
+            pl_ptr.append(len(planes))
+        tic_ptr.append(len(mv))
+    out.update(tic_ptr=np.array(tic_ptr, np.int64), moves=np.array(mv, np.int8), ended=np.array(ended, np.int8),
+               planes=np.array(planes, np.float32), pl_ptr=np.array(pl_ptr, np.int64))
+    for k in after:
+        out["after_" + k] = np.array(after[k], np.int32)
+    np.savez_compressed(os.path.join(HERE, "edge_sequences.npz"), **out)
+    print("edge_sequences: %d scenarios, %d tics, min health %d" % (len(cases), len(mv), min(c["min_health"] for c in cases)))
+
+
+# ---------------------------------------------------------------------------------------------
 # Deterministic stub value function, defined on the plane bytes; the oracle (og_plane_key, og_stub_value,
 # og_obstacle_mask) and the CUDA engine implement the same definition independently.
 M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
@@ -337,18 +418,53 @@ class StubNet:
         return V
 
 
-def gen_mcts(name, H, W, S, health_dec, G, base, training, D, breadth, root_turns, seed):
+def gen_mcts(name, H, W, S, health_dec, G, base, training, D, breadth, root_turns, seed, custom=None, warm_tics=0,
+             need_nonpositive_health=False):
+    """custom: list of G (snakes, last_moves, food) specs for build_ref_game -- the run starts from hand-built states (the
+    tests then take the start state from the t0_before_* dumps: `custom` = 1 in the fixture).
+    warm_tics: uniform-random root tics played before the search starts (mid-game start: fewer live snakes, deeper
+    sub-games at 19x19x8, agent.py:45); games that end while warming up are re-created."""
     pyrandom.seed(seed)
     np.random.seed(seed)
     net = StubNet()
     agent = ra.Agent(net, base, training, D, breadth)
     parallel = min(8, breadth)
     epochs = breadth // parallel
-    games = {i: rg.Game(i, H, W, S, health_dec) for i in range(G)}
-    init = dict(start=[[s.head.position for s in games[i].snakes] for i in range(G)],
-                last=[[games[i].last_moves[k] for k in range(S)] for i in range(G)],
-                food=[sorted(games[i].food) + [(-1, -1)] * (S + 1 - len(games[i].food)) for i in range(G)],
-                nfood=[len(games[i].food) for i in range(G)])
+    if custom is not None:
+        assert len(custom) == G
+        games = {i: build_ref_game(H, W, S, health_dec, custom[i][0], custom[i][1], custom[i][2], chance=0.15, gid=i) for i in range(G)}
+    else:
+        games = {i: rg.Game(i, H, W, S, health_dec) for i in range(G)}
+    if warm_tics:
+        wr = np.random.default_rng(seed + 1000)
+        for i in range(G):
+            while True:
+                g = rg.Game(i, H, W, S, health_dec)
+                ok = True
+                for _ in range(warm_tics[i] if isinstance(warm_tics, (list, tuple)) else warm_tics):
+                    if g.tic(wr.integers(0, 3, size=len(g.snakes)).tolist()) != 0:
+                        ok = False
+                        break
+                if ok:
+                    break
+            games[i] = g
+            # counters restart: the fixtures compare the six log counters from the start of the recorded run
+            g.wall_collision = g.body_collision = g.head_collision = g.starvation = g.food_eaten = g.game_length = 0
+    nonpos = dict(n=0)
+    orig_tic = rg.Game.tic
+
+    def tic_probe(self, moves, show=False):
+        r = orig_tic(self, moves, show)
+        nonpos["n"] += sum(1 for sn in self.snakes if sn.health <= 0)
+        return r
+    rg.Game.tic = tic_probe
+    if custom is not None or warm_tics:
+        init = dict(start=np.zeros((G, S, 2)), last=np.zeros((G, S)), food=np.zeros((G, S + 1, 2)), nfood=np.zeros(G))
+    else:
+        init = dict(start=[[s.head.position for s in games[i].snakes] for i in range(G)],
+                    last=[[games[i].last_moves[k] for k in range(S)] for i in range(G)],
+                    food=[sorted(games[i].food) + [(-1, -1)] * (S + 1 - len(games[i].food)) for i in range(G)],
+                    nfood=[len(games[i].food) for i in range(G)])
 
     # hooks: capture (ids, moves) of every MCTSAgent.make_moves call, epoch boundaries via MCTSMPGameRunner.run
     calls = []
@@ -423,7 +539,11 @@ def gen_mcts(name, H, W, S, health_dec, G, base, training, D, breadth, root_turn
     finally:
         ra.MCTSAgent.make_moves = orig_mm
         rr.MCTSMPGameRunner.run = orig_run
+        rg.Game.tic = orig_tic
+    if need_nonpositive_health:
+        assert nonpos["n"] > 0, "no snake ended a (sub-)game tic alive with health <= 0"
     out = dict(H=H, W=W, S=S, health_dec=health_dec, G=G, base=base, training=int(training), D=D, breadth=breadth,
+               custom=int(custom is not None or bool(warm_tics)), nonpositive_health_tics=nonpos["n"],
                n_turns=len(per_turn), init_start=np.array(init["start"], np.int32), init_last=np.array(init["last"], np.int32),
                init_food=np.array(init["food"], np.int32), init_nfood=np.array(init["nfood"], np.int32))
     for t, d in enumerate(per_turn):
@@ -436,7 +556,8 @@ def gen_mcts(name, H, W, S, health_dec, G, base, training, D, breadth, root_turn
     if training:
         out["records"] = np.array([np.ascontiguousarray(r) for r in agent.records], np.float32)
     np.savez_compressed(os.path.join(HERE, "mcts_%s.npz" % name), **out)
-    print("mcts_%s: %d root turns, %d evals, table %d" % (name, len(per_turn), sum(net.calls), len(agent.cached_values)))
+    print("mcts_%s: %d root turns, %d evals, table %d, %d snake-tics with health <= 0" % (
+        name, len(per_turn), sum(net.calls), len(agent.cached_values), nonpos["n"]))
 
 
 def gen_funcs():
@@ -511,7 +632,39 @@ def gen_replay(name, H, W, S, health_dec, n_games, seed, max_tics=400):
     print("replay_%s: %d games, %d tics" % (name, n_games, len(t_moves)))
 
 
+def neg_health_games():
+    """four root games in which snake 0 (length 4, low health) faces snake 1 (length 3) two cells away: in every sub-game
+    where both go straight, snake 0 wins the head-on and lives on with health <= 0 (game.py:156-165)"""
+    far = (100, [(9, 6), (9, 5), (9, 4)])
+    far2 = (100, [(7, 4), (7, 5), (7, 6)])
+    A4 = [(5, 4), (5, 3), (5, 2), (5, 1)]
+    B3 = [(5, 6), (5, 7), (5, 8)]
+    A4v = [(4, 5), (3, 5), (2, 5), (1, 5)]         # the same meeting, vertical: heading down / up
+    B3v = [(6, 5), (7, 5), (8, 5)]
+    return [([(5, A4), (100, B3), far, far2], [1, 3, 1, 3], [(1, 9), (4, 5)]),
+            ([(9, A4), (100, B3), far, None], [1, 3, 1, 0], [(1, 9)]),
+            ([(2, A4v), (100, B3v), None, (100, [(9, 9), (9, 8), (9, 7)])], [2, 0, 0, 1], [(1, 1), (5, 6)]),
+            ([(100, B3), (7, A4), far, far2], [3, 1, 1, 3], [(1, 9), (6, 5)])]
+
+
+def gen_round2():
+    """fixtures added in round 2 (all from the unmodified reference)"""
+    gen_edge_sequences()
+    # sub-games in which a head-on winner lives on with health <= 0, at the trainer's health_dec 9 and 3
+    gen_mcts("11x11x4_neghealth_dec9", 11, 11, 4, 9, G=4, base=2, training=True, D=8, breadth=24, root_turns=4, seed=31,
+             custom=neg_health_games(), need_nonpositive_health=True)
+    gen_mcts("11x11x4_neghealth_dec3", 11, 11, 4, 3, G=4, base=3, training=True, D=8, breadth=16, root_turns=3, seed=32,
+             custom=neg_health_games(), need_nonpositive_health=True)
+    # 19x19x8 from a mid-game start: <= 5 live snakes, so sub-games are deeper than one tic (agent.py:45), with deaths,
+    # evictions (agent.py:101-110) and > 1,000 evaluations
+    gen_mcts("19x19x8_mid", 19, 19, 8, 1, G=3, base=2, training=True, D=8, breadth=16, root_turns=12, seed=33,
+             warm_tics=[10, 18, 30])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        gen_round2()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "replay":      # only the fixtures added after the first generation
         gen_replay("11x11x4", 11, 11, 4, 1, 25, seed=21)
         gen_replay("7x7x8", 7, 7, 8, 1, 10, seed=22)
@@ -529,5 +682,6 @@ if __name__ == "__main__":
     gen_mcts("7x7x4_dec9", 7, 7, 4, 9, G=2, base=3, training=True, D=4, breadth=8, root_turns=10, seed=13)
     gen_mcts("19x19x8", 19, 19, 8, 1, G=1, base=2, training=True, D=8, breadth=8, root_turns=3, seed=14)
     gen_mcts("11x11x4_b5", 11, 11, 4, 1, G=2, base=2, training=True, D=8, breadth=5, root_turns=4, seed=15)
+    gen_round2()
     gen_replay("11x11x4", 11, 11, 4, 1, 25, seed=21)
     gen_replay("7x7x8", 7, 7, 8, 1, 10, seed=22)

@@ -10,7 +10,10 @@ from tests.test_gpu_env import _engine, init_dump
 
 pytestmark = pytest.mark.gpu
 
-MCTS = ["11x11x4_train", "11x11x4_eval", "7x7x4_dec9", "19x19x8", "11x11x4_b5"]
+# the last three (round 2) start from hand-built / mid-game states: sub-games in which a head-on winner lives on with
+# health <= 0 at health_dec 9 and 3 (game.py:156-165), and 19x19x8 with 3-4 live snakes (depth 4-6, deaths, evictions)
+MCTS = ["11x11x4_train", "11x11x4_eval", "7x7x4_dec9", "19x19x8", "11x11x4_b5",
+        "11x11x4_neghealth_dec9", "11x11x4_neghealth_dec3", "19x19x8_mid"]
 
 
 def rows_of(eng_or_dumps, G, S, alive_fn):
@@ -30,9 +33,15 @@ def test_search_replay_against_reference(name):
     D, breadth, training = int(z["D"]), int(z["breadth"]), bool(z["training"])
     eng = _engine(side=side, snakes=S, health_dec=dec, games=G, seed=5, max_depth=D, max_breadth=breadth,
                   softmax_base=float(z["base"]), training=training, table_log2=16)
+    custom = "custom" in z.files and int(z["custom"]) == 1
     for gi in range(G):
-        nf = int(z["init_nfood"][gi])
-        eng.set_state(gi, init_dump(side, S, z["init_start"][gi], z["init_last"][gi], z["init_food"][gi][:nf]))
+        if custom:      # hand-built or mid-game start: the state before the first recorded root turn
+            eng.set_state(gi, {k: z["t0_before_%s" % k][gi] for k in ("snake", "owner", "dist", "food", "counters")})
+        else:
+            nf = int(z["init_nfood"][gi])
+            eng.set_state(gi, init_dump(side, S, z["init_start"][gi], z["init_last"][gi], z["init_food"][gi][:nf]))
+    if "nonpositive_health_tics" in z.files and "neghealth" in name:
+        assert int(z["nonpositive_health_tics"]) > 0
     info = eng.search_info()
     assert info["P"] == min(8, breadth) and info["epochs"] == breadth // min(8, breadth)
     for t in range(int(z["n_turns"])):

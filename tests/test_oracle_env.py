@@ -57,6 +57,37 @@ def test_edge_cases():
             assert np.array_equal(g.make_state(k).view(np.uint32), pa[k].view(np.uint32)), name
 
 
+def test_edge_sequences():
+    """multi-tic scenarios recorded from the reference: a head-on winner ends a tic alive with health <= 0 (game.py:156-165 is an
+    elif chain), then starves / eats / hits the wall / wins again; health_dec 9, 3 and 1"""
+    z = load("edge_sequences.npz")
+    keys = ("snake", "owner", "dist", "food", "counters")
+    assert int(z["min_health"].min()) < 0
+    for i, name in enumerate(z["names"]):
+        g = orc.OracleGame(11, 11, 4, int(z["health_dec"][i]))
+        g.load_dump({k: z["before_" + k][i] for k in keys})
+        for t in range(int(z["tic_ptr"][i]), int(z["tic_ptr"][i + 1])):
+            n = g.n_live
+            ended = g.tic(z["moves"][t][:n].astype(np.int32), spawn_mode=0)
+            assert ended == int(z["ended"][t]), (name, t)
+            assert_dump_equal(g.dump(), {k: z["after_" + k][t] for k in keys}, "%s tic %d" % (name, t))
+            pl = z["planes"][int(z["pl_ptr"][t]):int(z["pl_ptr"][t + 1])]
+            assert len(pl) == (0 if ended else g.n_live), name
+            for k in range(len(pl)):
+                assert np.array_equal(g.make_state(k).view(np.uint32), pl[k].view(np.uint32)), (name, t, k)
+
+
+def test_food_chance_zero_never_spawns():
+    """game.py:130 `if self.food_spawn_chance > 0.0`: with chance 0 no food is ever spawned, not even on a board without food"""
+    g = orc.OracleGame(11, 11, 2, 1)
+    g.init_explicit([(1, 1), (9, 9)], [1, 3], [])
+    for _ in range(6):
+        g.tic(np.array([1, 1], np.int32), spawn_mode=2, chance=0.0, seed=3)
+        assert g.dump()["food"].sum() == 0
+    g.tic(np.array([2, 2], np.int32), spawn_mode=2, chance=1e-12, seed=3)    # any positive chance spawns on a board without food
+    assert g.dump()["food"].sum() == 1
+
+
 def test_funcs():
     z = load("funcs.npz")
     Z = z["Z"]

@@ -6,17 +6,22 @@ import pytest
 from oracle import oracle as orc
 from tests.helpers import assert_dump_equal, load
 
-MCTS = ["11x11x4_train", "11x11x4_eval", "7x7x4_dec9", "19x19x8", "11x11x4_b5"]
+MCTS = ["11x11x4_train", "11x11x4_eval", "7x7x4_dec9", "19x19x8", "11x11x4_b5",
+        "11x11x4_neghealth_dec9", "11x11x4_neghealth_dec3", "19x19x8_mid"]
 
 
 def replay_reference_turns(z, make_agent, on_turn):
     """Drives root games from the fixture; calls on_turn(t, games(list of OracleGame, live), z) each root turn."""
     H, W, S, dec, G = (int(z[k]) for k in ("H", "W", "S", "health_dec", "G"))
     games = {}
+    custom = "custom" in z.files and int(z["custom"]) == 1
     for gi in range(G):
         g = orc.OracleGame(H, W, S, dec)
-        nf = int(z["init_nfood"][gi])
-        g.init_explicit(z["init_start"][gi], z["init_last"][gi], z["init_food"][gi][:nf])
+        if custom:      # hand-built or mid-game start: the state before the first recorded root turn
+            g.load_dump({k: z["t0_before_%s" % k][gi] for k in ("snake", "owner", "dist", "food", "counters")})
+        else:
+            nf = int(z["init_nfood"][gi])
+            g.init_explicit(z["init_start"][gi], z["init_last"][gi], z["init_food"][gi][:nf])
         g.set_ids(gi, 0)
         games[gi] = g
     for t in range(int(z["n_turns"])):
