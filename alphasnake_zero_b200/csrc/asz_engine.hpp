@@ -19,6 +19,20 @@ bool cuda_ok(cudaError_t err, const char* what);
 
 struct SearchState;   // asz_mcts.cu
 
+// Every entry point that takes an engine (or a network) runs on THAT object's device, whatever device is current in the
+// calling thread ("one engine per GPU": several engines on different GPUs may live in one process).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+constexpr int kMaxDevices = 64;   // per-device "kernel attributes configured" flags (function attributes are per device)
+
 // Device-resident game set: one record per game, structure-of-arrays over games.
 //   cells  [n][PC]  u16 stamps (asz_common.cuh)
 //   snakes [n][8]   u64 packed snake records
@@ -35,6 +49,7 @@ struct GameSet {
 struct asz_engine {
   asz_config cfg;
   int device = 0;
+  int n_sm = 0;          // multiprocessors of `device`
   int pc = 0;            // padded cells per game
   int plane = 0;         // floats per plane
   uint32_t chance_thresh = 0;

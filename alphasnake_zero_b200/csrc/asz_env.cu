@@ -35,6 +35,7 @@ struct EnvParams {
   int* work_counter;   // dynamic game scheduler of the persistent kernel (zeroed before the launch)
   unsigned long long* prof;   // ASZ_ENV_PROFILE builds only: per-phase cycle sums (tools/env_profile.py)
   int hints;           // 1: L2 policies (planes evict_first, game records evict_last), 0: default policy everywhere
+  int device, n_sm;    // the engine's device and its multiprocessor count (grid size of the persistent kernel)
 };
 
 // Phase timers for the measurement build (nvcc -DASZ_ENV_PROFILE, tools/env_profile.py); they compile to nothing otherwise.
@@ -318,21 +319,19 @@ struct EnvLaunch {
   }
   template <int MINB, bool HINTS, bool ACTS>
   static int launch(const EnvParams& p, cudaStream_t st) {
-    static bool configured = false;
-    static int n_sm = 0;
-    if (!configured) {
+    // function attributes are per device: one flag per device and kernel instantiation (the caller holds a DeviceGuard)
+    static bool configured[kMaxDevices] = {false};
+    const int dev = p.device;
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
       if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_bytes()), "cudaFuncSetAttribute(env_step_kernel)"))
         return ASZ_ERR_CUDA;
       if (!cuda_ok(cudaFuncSetAttribute(env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
         return ASZ_ERR_CUDA;
-      int dev = 0;
-      if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return ASZ_ERR_CUDA;
-      if (!cuda_ok(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return ASZ_ERR_CUDA;
-      configured = true;
+      if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
-    const int blocks = std::min((p.G + WARPS - 1) / WARPS, n_sm * MINB);
+    const int blocks = std::min((p.G + WARPS - 1) / WARPS, p.n_sm * MINB);
     env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
     return cuda_ok(cudaGetLastError(), "env_step_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
   }
@@ -387,6 +386,7 @@ static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   { const char* v = getenv("ASZ_ENV_HINTS_HOST"); e->host_hints = v ? atoi(v) : 0; }
   e->step_hints = e->device_hints;
   ASZ_CUDA(cudaGetDevice(&e->device));
+  ASZ_CUDA(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, e->device));
   e->pc = pc_of(cfg->side);
   e->plane = (2 * cfg->side - 1) * (2 * cfg->side - 1) * 3;
   double th = (double)cfg->food_chance * 4294967296.0;
@@ -437,6 +437,7 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
 
 int asz_engine_destroy(asz_engine* e) {
   if (!e) return ASZ_OK;
+  DeviceGuard guard(e->device);
   search_destroy(e);
   gameset_free(e->root);
   cudaFree(e->planes); cudaFree(e->row_ids); cudaFree(e->row_count); cudaFree(e->actions); cudaFree(e->spawn_cells);
@@ -447,6 +448,7 @@ int asz_engine_destroy(asz_engine* e) {
 
 int asz_reset(asz_engine* e, void* stream) {
   if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   ASZ_CUDA(cudaMemsetAsync(e->totals, 0, 32 * sizeof(unsigned long long), st));
   switch (e->cfg.side) {
@@ -467,8 +469,10 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   if ((a->flags & ASZ_STEP_TIC) && !(a->flags & ASZ_STEP_RANDOM_ACT) && ((uintptr_t)a->d_actions & 7u)) { set_error("d_actions must be 8-byte aligned"); return ASZ_ERR_ARG; }
   if ((a->flags & ASZ_STEP_TIC) && a->spawn_mode == ASZ_SPAWN_REPLAY && !a->d_spawn_cells) { set_error("d_spawn_cells is null"); return ASZ_ERR_ARG; }
   if (a->spawn_mode < 0 || a->spawn_mode > 2) { set_error("bad spawn_mode"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   EnvParams p;
+  p.device = e->device; p.n_sm = e->n_sm;
   p.cells = e->root.cells; p.snakes = e->root.snakes; p.meta = e->root.meta;
   p.G = e->cfg.games; p.S = e->cfg.snakes; p.health_dec = e->cfg.health_dec;
   p.flags = a->flags; p.spawn_mode = a->spawn_mode; p.chance_thresh = e->chance_thresh; p.seed = e->cfg.seed;
@@ -497,6 +501,7 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
                       const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, int32_t* h_row_count,
                       float* h_planes, int32_t* h_row_ids, void* stream) {
   if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t G = (size_t)e->cfg.games;
   if ((flags & ASZ_STEP_TIC) && !(flags & ASZ_STEP_RANDOM_ACT)) {
@@ -547,6 +552,7 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
 
 int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
   if (!e || !h_totals) { set_error("null argument"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   ASZ_CUDA(cudaDeviceSynchronize());
   ASZ_CUDA(cudaMemcpy(h_totals, e->totals, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return ASZ_OK;
@@ -554,6 +560,7 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
 
 int asz_internal_profile(asz_engine* e, uint64_t* h_cycles) {
   if (!e || !h_cycles) { set_error("null argument"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   ASZ_CUDA(cudaDeviceSynchronize());
   ASZ_CUDA(cudaMemcpy(h_cycles, e->totals + 16, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   ASZ_CUDA(cudaMemset(e->totals + 16, 0, 8 * sizeof(uint64_t)));
@@ -639,11 +646,13 @@ static int gs_set_state(const asz_config& cfg, int pc, GameSet& gs, int32_t game
 int asz_get_state(asz_engine* e, int32_t game, int32_t* h_snake, int32_t* h_owner, int32_t* h_dist, int32_t* h_food,
                   int32_t* h_counters) {
   if (!e || !h_snake || !h_owner || !h_dist || !h_food || !h_counters) { set_error("null argument"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   return gs_get_state(e->cfg, e->pc, e->root, game, h_snake, h_owner, h_dist, h_food, h_counters);
 }
 int asz_set_state(asz_engine* e, int32_t game, const int32_t* h_snake, const int32_t* h_owner, const int32_t* h_dist,
                   const int32_t* h_food, const int32_t* h_counters) {
   if (!e || !h_snake || !h_owner || !h_dist || !h_food || !h_counters) { set_error("null argument"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   return gs_set_state(e->cfg, e->pc, e->root, game, h_snake, h_owner, h_dist, h_food, h_counters);
 }
 

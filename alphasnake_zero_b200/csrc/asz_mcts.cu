@@ -19,6 +19,7 @@
 // eval-batch index while the value is pending (agent.py:184 stores None for the same purpose).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -69,6 +70,10 @@ struct SearchState {
   uint32_t root_turn = 0;         // current root turn (1-based while a search is open)
   int epoch = -1, step = 0;
   bool open = false;
+  // host copies of stats[ST_OCCUPIED], stats[ST_OVERFLOW] (refreshed wherever the host synchronises anyway)
+  unsigned long long h_occ_ovf[2] = {0, 0};
+  unsigned long long overflow_reported = 0;   // overflow count already turned into an error
+  unsigned long long n_compactions = 0, n_mid_compactions = 0;   // table compactions: all / between two epochs of a turn
 };
 
 // ---- table ------------------------------------------------------------------------------------------------------
@@ -449,12 +454,14 @@ __global__ void policy_debug_kernel(const float* z, const double* u, int n, floa
 }
 
 // ---- table maintenance --------------------------------------------------------------------------------------------
-__global__ void table_rebuild_kernel(const Table src, Table dst, uint32_t cur_turn, int D, unsigned long long* occupied) {
+// ref_turn: the root turn whose END decides eviction (agent.py:101-110): the current turn when called from asz_search_finish, the
+// previous one when the table is compacted between two epochs of a turn (entries touched in this turn have age 0 either way)
+__global__ void table_rebuild_kernel(const Table src, Table dst, uint32_t ref_turn, int D, unsigned long long* occupied) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= src.cap) return;
   const uint64_t k0 = src.key[i];
   if (k0 == 0ull) return;
-  if ((int)(cur_turn - src.touch[i]) > D) return;   // evicted at the end of this turn (agent.py:101-110)
+  if ((int)(ref_turn - src.touch[i]) > D) return;   // evicted (agent.py:101-110)
   const uint64_t k1 = src.chk[i];
   const uint64_t mask = dst.cap - 1;
   uint64_t h = fmix64(k1 ^ (k0 >> 7)) & mask;
@@ -580,6 +587,23 @@ static SearchParams make_params(asz_engine* e) {
   return p;
 }
 
+// Copies the live entries into the spare table and swaps (slots held by evicted entries are given back).
+static int table_compact(asz_engine* e, uint32_t ref_turn, cudaStream_t st) {
+  SearchState* s = e->search;
+  if (!s->tab_alt.key) { int rc = table_alloc(s->tab_alt, s->tab.log2cap); if (rc != ASZ_OK) return rc; }
+  ASZ_CUDA(cudaMemsetAsync(s->tab_alt.key, 0, s->tab_alt.cap * sizeof(uint64_t), st));
+  ASZ_CUDA(cudaMemsetAsync(s->tab_alt.touch, 0xFF, s->tab_alt.cap * sizeof(uint32_t), st));
+  ASZ_CUDA(cudaMemsetAsync(&s->stats[ST_OCCUPIED], 0, sizeof(unsigned long long), st));
+  table_rebuild_kernel<<<(unsigned)((s->tab.cap + 255) / 256), 256, 0, st>>>(s->tab, s->tab_alt, ref_turn, e->cfg.max_depth,
+                                                                            &s->stats[ST_OCCUPIED]);
+  if (!cuda_ok(cudaGetLastError(), "table_rebuild_kernel")) return ASZ_ERR_CUDA;
+  std::swap(s->tab, s->tab_alt);
+  s->h_occ_ovf[0] = 0;
+  s->n_compactions += 1;
+  if (ref_turn != s->root_turn) s->n_mid_compactions += 1;
+  return ASZ_OK;
+}
+
 template <int SIDE>
 struct SearchLaunch {
   static constexpr int WARPS = (SIDE >= 19) ? 4 : 8;
@@ -589,13 +613,13 @@ struct SearchLaunch {
     search_epoch_begin_kernel<SIDE><<<p.n_sub, 64, 0, st>>>(p);
     return cuda_ok(cudaGetLastError(), "search_epoch_begin_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
   }
-  static int step(const SearchParams& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+  static int step(const SearchParams& p, int dev, cudaStream_t st) {
+    static bool configured[kMaxDevices] = {false};   // function attributes are per device
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
       if (!cuda_ok(cudaFuncSetAttribute(search_step_kernel<SIDE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_bytes()), "cudaFuncSetAttribute(search_step_kernel)"))
         return ASZ_ERR_CUDA;
-      configured = true;
+      if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
     const int blocks = (p.n_sub + WARPS - 1) / WARPS;
     search_step_kernel<SIDE, WARPS><<<blocks, WARPS * 32, smem_bytes(), st>>>(p);
@@ -611,6 +635,7 @@ extern "C" {
 
 int asz_search_begin(asz_engine* e, void* stream) {
   if (!e || !e->search) { set_error("search is not configured (max_breadth == 0)"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   if (s->open) { set_error("asz_search_begin: a search is already open"); return ASZ_ERR_STATE; }
   (void)stream;
@@ -621,10 +646,18 @@ int asz_search_begin(asz_engine* e, void* stream) {
 
 int asz_search_epoch_begin(asz_engine* e, void* stream) {
   if (!e || !e->search || !e->search->open) { set_error("no open search"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   if (s->epoch + 1 >= s->E) { set_error("all epochs of this root turn are done"); return ASZ_ERR_STATE; }
   s->epoch += 1; s->step = 0;
   cudaStream_t st = (cudaStream_t)stream;
+  // Evicted entries keep their slots until a compaction, so a long root turn could fill the table on its own: between two
+  // epochs no path, row or pending evaluation refers to a slot, and a table more than 3/4 full (as of the last host
+  // synchronisation) is compacted right here
+  if (s->h_occ_ovf[0] * 4 > s->tab.cap * 3) {
+    const int rc = table_compact(e, s->root_turn - 1u, st);
+    if (rc != ASZ_OK) return rc;
+  }
   const SearchParams p = make_params(e);
   int rc;
   switch (e->cfg.side) {
@@ -639,6 +672,7 @@ int asz_search_epoch_begin(asz_engine* e, void* stream) {
 
 int asz_search_step_probe(asz_engine* e, int32_t* h_n_miss, void* stream) {
   if (!e || !e->search || !e->search->open || e->search->epoch < 0) { set_error("no open epoch"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   if (s->step > s->Dmax) { set_error("epoch already finished"); return ASZ_ERR_STATE; }
   s->step += 1;
@@ -647,13 +681,14 @@ int asz_search_step_probe(asz_engine* e, int32_t* h_n_miss, void* stream) {
   const SearchParams p = make_params(e);
   int rc;
   switch (e->cfg.side) {
-    case 7: rc = SearchLaunch<7>::step(p, st); break;
-    case 11: rc = SearchLaunch<11>::step(p, st); break;
-    default: rc = SearchLaunch<19>::step(p, st); break;
+    case 7: rc = SearchLaunch<7>::step(p, e->device, st); break;
+    case 11: rc = SearchLaunch<11>::step(p, e->device, st); break;
+    default: rc = SearchLaunch<19>::step(p, e->device, st); break;
   }
   if (rc != ASZ_OK) return rc;
   if (h_n_miss) {
     ASZ_CUDA(cudaMemcpyAsync(h_n_miss, s->n_miss, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ASZ_CUDA(cudaMemcpyAsync(s->h_occ_ovf, &s->stats[ST_OCCUPIED], sizeof s->h_occ_ovf, cudaMemcpyDeviceToHost, st));
     ASZ_CUDA(cudaStreamSynchronize(st));
     if (*h_n_miss > s->max_rows) *h_n_miss = s->max_rows;
   }
@@ -662,6 +697,7 @@ int asz_search_step_probe(asz_engine* e, int32_t* h_n_miss, void* stream) {
 
 int asz_search_step_sample(asz_engine* e, const float* d_values, uint8_t* d_trace, int32_t trace_mode, void* stream) {
   if (!e || !e->search || !e->search->open || e->search->step < 1) { set_error("no probed step"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   if (s->step > s->Dmax) return ASZ_OK;   // the closing probe of an epoch has no rows
   if (trace_mode != 0 && !d_trace) { set_error("trace_mode set but d_trace is null"); return ASZ_ERR_ARG; }
@@ -675,6 +711,7 @@ int asz_search_step_sample(asz_engine* e, const float* d_values, uint8_t* d_trac
 
 int asz_search_stub_values(asz_engine* e, void* stream) {
   if (!e || !e->search) { set_error("search is not configured"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   const int n = s->max_rows;   // the kernel reads the live count from device memory: no host sync
   stub_value_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->eval_keys, s->eval_planes, s->n_miss, e->cfg.side,
@@ -684,6 +721,7 @@ int asz_search_stub_values(asz_engine* e, void* stream) {
 
 int asz_obstacle_mask(asz_engine* e, const float* d_planes, int32_t n, float* d_values, void* stream) {
   if (!e || !d_planes || !d_values) { set_error("null argument"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
   if (n <= 0) return ASZ_OK;
   obstacle_mask_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_planes, n, e->cfg.side, e->cfg.numpy1_mask, d_values);
   return cuda_ok(cudaGetLastError(), "obstacle_mask_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
@@ -699,6 +737,7 @@ int asz_debug_policy(const float* d_z, const double* d_u, int32_t n, float base,
 
 int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_q, uint8_t* d_root_moves, void* stream) {
   if (!e || !e->search || !e->search->open) { set_error("no open search"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   cudaStream_t st = (cudaStream_t)stream;
   SearchParams p = make_params(e);
@@ -710,18 +749,22 @@ int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_
   if (!cuda_ok(cudaGetLastError(), "search_root_kernel")) return ASZ_ERR_CUDA;
   s->open = false;
   // compaction when the table is more than half full of (mostly evicted) entries
-  unsigned long long occ = 0;
-  ASZ_CUDA(cudaMemcpyAsync(&occ, &s->stats[ST_OCCUPIED], sizeof occ, cudaMemcpyDeviceToHost, st));
+  static_assert(ST_OVERFLOW == ST_OCCUPIED + 1, "occupied and overflow are read with one copy");
+  ASZ_CUDA(cudaMemcpyAsync(s->h_occ_ovf, &s->stats[ST_OCCUPIED], sizeof s->h_occ_ovf, cudaMemcpyDeviceToHost, st));
   ASZ_CUDA(cudaStreamSynchronize(st));
-  if (occ * 2 > s->tab.cap) {
-    if (!s->tab_alt.key) { int rc = table_alloc(s->tab_alt, s->tab.log2cap); if (rc != ASZ_OK) return rc; }
-    ASZ_CUDA(cudaMemsetAsync(s->tab_alt.key, 0, s->tab_alt.cap * sizeof(uint64_t), st));
-    ASZ_CUDA(cudaMemsetAsync(s->tab_alt.touch, 0xFF, s->tab_alt.cap * sizeof(uint32_t), st));
-    ASZ_CUDA(cudaMemsetAsync(&s->stats[ST_OCCUPIED], 0, sizeof(unsigned long long), st));
-    table_rebuild_kernel<<<(unsigned)((s->tab.cap + 255) / 256), 256, 0, st>>>(s->tab, s->tab_alt, s->root_turn, e->cfg.max_depth,
-                                                                              &s->stats[ST_OCCUPIED]);
-    if (!cuda_ok(cudaGetLastError(), "table_rebuild_kernel")) return ASZ_ERR_CUDA;
-    std::swap(s->tab, s->tab_alt);
+  if (s->h_occ_ovf[0] * 2 > s->tab.cap) {
+    const int rc = table_compact(e, s->root_turn, st);
+    if (rc != ASZ_OK) return rc;
+  }
+  // A probe that found no slot dropped its row: that snake then played "straight" in its sub-game and the search result is
+  // not the reference's.  Never silent: the turn's outputs are written, but the call fails.
+  if (s->h_occ_ovf[1] > s->overflow_reported) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "Q table overflow: %llu probes found no free slot in 2^%d slots this root turn (raise table_log2)",
+             s->h_occ_ovf[1] - s->overflow_reported, s->tab.log2cap);
+    s->overflow_reported = s->h_occ_ovf[1];
+    set_error(msg);
+    return ASZ_ERR_CAPACITY;
   }
   return ASZ_OK;
 }
@@ -770,12 +813,14 @@ int asz_search_run_net(asz_engine* e, asz_net* net, uint8_t* d_trace, int32_t tr
 
 int asz_search_clear(asz_engine* e, void* stream) {
   if (!e || !e->search) { set_error("search is not configured"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   cudaStream_t st = (cudaStream_t)stream;
   ASZ_CUDA(cudaMemsetAsync(s->tab.key, 0, s->tab.cap * sizeof(uint64_t), st));
   ASZ_CUDA(cudaMemsetAsync(s->tab.touch, 0xFF, s->tab.cap * sizeof(uint32_t), st));
   ASZ_CUDA(cudaMemsetAsync(s->stats, 0, ST_COUNT * sizeof(unsigned long long), st));
   s->root_turn = 0; s->open = false; s->epoch = -1; s->step = 0;
+  s->h_occ_ovf[0] = s->h_occ_ovf[1] = 0; s->overflow_reported = 0; s->n_compactions = s->n_mid_compactions = 0;
   return ASZ_OK;
 }
 
@@ -794,13 +839,16 @@ uint8_t* asz_search_root_moves(asz_engine* e) { return (e && e->search) ? e->sea
 
 int asz_search_stats(asz_engine* e, uint64_t* h_stats) {
   if (!e || !e->search || !h_stats) { set_error("search is not configured"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   ASZ_CUDA(cudaDeviceSynchronize());
   ASZ_CUDA(cudaMemcpy(h_stats, e->search->stats, ST_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  h_stats[10] = e->search->n_compactions; h_stats[11] = e->search->n_mid_compactions;   // host-side counts
   return ASZ_OK;
 }
 
 int asz_search_table_dump(asz_engine* e, int32_t cap, uint64_t* h_keys, float* h_w, float* h_n, int32_t* h_age, int32_t* h_count) {
   if (!e || !e->search || !h_count) { set_error("search is not configured"); return ASZ_ERR_STATE; }
+  DeviceGuard guard(e->device);
   SearchState* s = e->search;
   int* d_count; uint64_t* d_keys; float *d_w, *d_n; int32_t* d_age;
   const size_t c = (size_t)std::max(cap, 1);

@@ -145,12 +145,13 @@ class Engine:
         holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
         return torch.as_tensor(holder, device=self.device).view(dtype).view(*shape)
 
-    def search(self, value_fn=None, trace=None, trace_mode=0, root_trace=None, net=None):
+    def search(self, value_fn=None, trace=None, trace_mode=0, root_trace=None, net=None, sync_steps=False):
         """One root turn of the search for the engine's current root games.
         net: a NativeNet -- the whole root turn runs in one native call (asz_search_run_net), the product path.
         value_fn(planes[n, N, N, 3] float32 cuda) -> [n, 3] float32 cuda raw network outputs (the obstacle mask of
         AlphaNNet.v is applied here): a Python-driven loop for reference networks (tests).
-        Neither = the deterministic stub value function (no host sync in the loops).
+        Neither = the deterministic stub value function (no host sync in the loops; sync_steps=True drives the same stub
+        through the per-step calls, reading the miss count back every step like the network path does).
         trace: uint8 cuda tensor [epochs, max_steps, G*P, S]; trace_mode 0 none / 1 replay / 2 record.
         Returns (root_q [G, 8, 3] float32, root_moves [G, 8] uint8, 255 = no row) as views of engine buffers."""
         st = self.stream
@@ -158,7 +159,7 @@ class Engine:
         rp = C.c_void_p(root_trace.data_ptr()) if root_trace is not None else None
         if net is not None:
             check(self.L.asz_search_run_net(self.h, net.h, tp, trace_mode, rp, st))
-        elif value_fn is None:
+        elif value_fn is None and not sync_steps:
             check(self.L.asz_search_run_stub(self.h, tp, trace_mode, rp, st))
         else:
             info = self.search_info()
@@ -171,7 +172,9 @@ class Engine:
                 for step in range(1, info["max_steps"] + 2):
                     check(self.L.asz_search_step_probe(self.h, C.byref(n), st))
                     if step <= info["max_steps"]:
-                        if n.value > 0:
+                        if value_fn is None:
+                            check(self.L.asz_search_stub_values(self.h, st))
+                        elif n.value > 0:
                             v = value_fn(planes[:n.value])
                             values[:n.value].copy_(v)
                             check(self.L.asz_obstacle_mask(self.h, C.c_void_p(planes.data_ptr()), n.value,
@@ -189,7 +192,7 @@ class Engine:
         s = np.zeros(16, np.uint64)
         check(self.L.asz_search_stats(self.h, _np(s)))
         names = ("evals", "node_visits", "hits", "subgames", "subgame_tics", "collisions", "inserts", "recreated",
-                 "occupied", "overflow")
+                 "occupied", "overflow", "compactions", "mid_turn_compactions")
         return dict(zip(names, s.tolist()))
 
     def table(self, cap=None):

@@ -35,6 +35,9 @@ class Agent:
         qh = q.cpu().numpy()
         mvh = mv.cpu().numpy()
         moves = [int(mvh[g, s]) for g, s in ids]
+        if any(m > 2 for m in moves):      # a live snake without a searched row: never hand an arbitrary direction to the tic
+            from .._lib import AszError
+            raise AszError("search returned no move for a live snake (ids do not match the engine's live snakes)")
         if self.training:
             # agent.py:93-97: root states and their Q rows (snapshots; the reference stores aliases)
             planes, rows = eng.encode_rows()

@@ -15,14 +15,19 @@ class MPGameRunner:
         self.engine.reset()
 
     # Alice and Bob are agents using different nets
-    def run(self, Alice, Bob, Alice_snake_cnt=None):
+    def run(self, Alice, Bob, Alice_snake_cnt=None, spawn_trace=None, move_log=None):
+        """pit_mp_game_runner.py:14-63.  Extensions for trace replay (tests): spawn_trace[turn] = int32 [game_cnt] food cell
+        spawned in that turn's tic (-1 none) instead of the engine's RNG; move_log (a list) receives per turn a uint8
+        [game_cnt, 8] array of the moves played (255 = no move)."""
         eng = self.engine
         if Alice_snake_cnt is None:
             Alice_snake_cnt = self.snake_cnt // 2
         winners = [None] * self.game_cnt
         running = np.ones(self.game_cnt, bool)
         eng.step(tic=False, encode=True)
+        turn = -1
         while running.any():
+            turn += 1
             planes, rows = eng.encode_rows(refresh=False)
             rows = rows.astype(np.int64)
             g, s = rows // 8, rows % 8
@@ -34,7 +39,17 @@ class MPGameRunner:
             actions = np.ones((self.game_cnt, 8), np.uint8)
             actions[g[a_idx], s[a_idx]] = np.asarray(moves_a, np.uint8)
             actions[g[b_idx], s[b_idx]] = np.asarray(moves_b, np.uint8)
-            eng.step(actions=torch.from_numpy(actions).to(eng.device), spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=True)
+            if move_log is not None:
+                played = np.full((self.game_cnt, 8), 255, np.uint8)
+                played[g[a_idx], s[a_idx]] = np.asarray(moves_a, np.uint8)
+                played[g[b_idx], s[b_idx]] = np.asarray(moves_b, np.uint8)
+                move_log.append(played)
+            if spawn_trace is not None:
+                cells = torch.from_numpy(np.maximum(np.asarray(spawn_trace[turn], np.int32), -1)).to(eng.device)
+                eng.step(actions=torch.from_numpy(actions).to(eng.device), spawn_cells=cells, spawn_mode=_lib.SPAWN_REPLAY,
+                         tic=True, encode=True)
+            else:
+                eng.step(actions=torch.from_numpy(actions).to(eng.device), spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=True)
             ended = eng.ended.cpu().numpy().astype(bool)
             rw = eng.rewards.cpu().numpy()
             alive = eng.alive_mask().cpu().numpy()

@@ -163,7 +163,9 @@ int asz_search_epoch_begin(asz_engine* e, void* stream);
 int asz_search_step_probe(asz_engine* e, int32_t* h_n_miss, void* stream);
 /* d_values: [n_miss][3] float32 network outputs WITH the obstacle mask applied, or NULL = asz_search_eval_values() */
 int asz_search_step_sample(asz_engine* e, const float* d_values, uint8_t* d_trace, int32_t trace_mode, void* stream);
-/* d_root_q [games*8*3], d_root_moves [games*8] (255 = no row) or NULL to keep them in the engine's buffers */
+/* d_root_q [games*8*3], d_root_moves [games*8] (255 = no row) or NULL to keep them in the engine's buffers.
+ * Returns ASZ_ERR_CAPACITY (after writing the outputs and closing the turn) when the Q table overflowed during the turn:
+ * the dropped rows make the result differ from the reference's, so it is never silent. */
 int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_q, uint8_t* d_root_moves, void* stream);
 /* deterministic stub value function (value from the plane key + obstacle mask) on the queued planes; device side count */
 int asz_search_stub_values(asz_engine* e, void* stream);
@@ -189,7 +191,8 @@ float* asz_search_eval_values(asz_engine* e);   /* device [max eval rows][3] flo
 float* asz_search_root_q(asz_engine* e);        /* device [games*8][3] */
 uint8_t* asz_search_root_moves(asz_engine* e);  /* device [games*8] */
 /* h_stats[16] = evals, node visits, hits(unused), sub-games, sub-game tics, tag collisions, inserts, re-created,
- * occupied slots, overflow, ... ; synchronous */
+ * occupied slots, overflow (probes that found no free slot; asz_search_finish fails with ASZ_ERR_CAPACITY when this grew
+ * during the turn), table compactions, of which between two epochs of one turn, ... ; synchronous */
 int asz_search_stats(asz_engine* e, uint64_t* h_stats);
 /* live (not evicted) table entries: keys [cap*2], W [cap*3], N [cap*3], age [cap]; *h_count = live entries. Synchronous.
  * Replaces inspection of Agent.cached_values / total_rewards / visit_cnts / cache_hit (agent.py:16-19); Q = W / N. */

@@ -16,6 +16,8 @@ Fixtures (all numpy .npz, compressed):
   mcts_<name>.npz   reference Agent + MPGameRunner with a deterministic stub value function: recorded
                     in-tree moves, root moves, root Q, and the full (key, Q, W, N, age) tables per root turn
   funcs.npz         softermax / argmaxs / numpy.random.choice known answers
+  pit_<name>.npz    the reference's pit MPGameRunner.run(Alice, Bob, Alice_snake_cnt) with two stand-in value functions:
+                    start layouts, spawned food cells, every move, the winner list (incl. the early exit)
   replay_<name>.npz the text frames Game.tic(show=True) appends to replay.rep, with the dumps they were drawn from
 """
 import hashlib
@@ -632,6 +634,54 @@ def gen_replay(name, H, W, S, health_dec, n_games, seed, max_tics=400):
     print("replay_%s: %d games, %d tics" % (name, n_games, len(t_moves)))
 
 
+def gen_pit(name, H, S, health_dec, G, alice_cnt, seed):
+    """pit_mp_game_runner.py:14-63 with pit_agent.py:10-13 agents over two different stand-in value functions"""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests.helpers import KeyStubNet
+    import utils.pit_agent as rpa
+    import utils.pit_mp_game_runner as rp
+    pyrandom.seed(seed)
+    np.random.seed(seed)
+    runner = rp.MPGameRunner(H, H, S, health_dec, G)
+    games = runner.games
+    init = dict(start=[[s.head.position for s in games[i].snakes] for i in range(G)],
+                last=[[games[i].last_moves[k] for k in range(S)] for i in range(G)],
+                food=[sorted(games[i].food) + [(-1, -1)] * (S + 1 - len(games[i].food)) for i in range(G)],
+                nfood=[len(games[i].food) for i in range(G)])
+    spawn, moves = {}, {}
+    orig_tic = rg.Game.tic
+
+    def tic(self, mv, show=False):
+        t = self.game_length
+        live = [sn.id for sn in self.snakes]
+        _spawned.clear()
+        r = orig_tic(self, mv, show)
+        spawn[(self.id, t)] = -1 if not _spawned else _spawned[-1][0] * H + _spawned[-1][1]
+        for sid, m in zip(live, mv):
+            moves[(self.id, t, sid)] = int(m)
+        return r
+    rg.Game.tic = tic
+    try:
+        Alice, Bob = rpa.Agent(KeyStubNet(1)), rpa.Agent(KeyStubNet(0))
+        winners = runner.run(Alice, Bob, alice_cnt)
+    finally:
+        rg.Game.tic = orig_tic
+    T = max(t for (_, t) in spawn) + 1
+    sp = np.full((T, G), -2, np.int32)          # -2: the game was no longer running that turn
+    mv = np.full((T, G, 8), 255, np.uint8)
+    for (g, t), c in spawn.items():
+        sp[t, g] = c
+    for (g, t, sid), m in moves.items():
+        mv[t, g, sid] = m
+    out = dict(H=H, S=S, health_dec=health_dec, G=G, alice_cnt=-1 if alice_cnt is None else alice_cnt,
+               winners=np.array([-1 if w is None else w for w in winners], np.int32), spawn=sp, moves=mv,
+               init_start=np.array(init["start"], np.int32), init_last=np.array(init["last"], np.int32),
+               init_food=np.array(init["food"], np.int32), init_nfood=np.array(init["nfood"], np.int32))
+    np.savez_compressed(os.path.join(HERE, "pit_%s.npz" % name), **out)
+    early = sum(1 for g in range(G) if winners[g] is not None and (sp[:, g] != -2).sum() > 0)
+    print("pit_%s: %d games, %d turns, winners %s" % (name, G, T, np.bincount(out["winners"] + 1, minlength=S + 1).tolist()))
+
+
 def neg_health_games():
     """four root games in which snake 0 (length 4, low health) faces snake 1 (length 3) two cells away: in every sub-game
     where both go straight, snake 0 wins the head-on and lives on with health <= 0 (game.py:156-165)"""
@@ -657,6 +707,10 @@ def gen_round2():
              custom=neg_health_games(), need_nonpositive_health=True)
     # 19x19x8 from a mid-game start: <= 5 live snakes, so sub-games are deeper than one tic (agent.py:45), with deaths,
     # evictions (agent.py:101-110) and > 1,000 evaluations
+    gen_pit("1v1", 11, 2, 1, G=40, alice_cnt=None, seed=41)
+    gen_pit("2v2", 11, 4, 1, G=40, alice_cnt=None, seed=42)
+    gen_pit("1v3", 11, 4, 1, G=30, alice_cnt=1, seed=43)
+    gen_pit("3v1_7x7", 7, 4, 3, G=30, alice_cnt=3, seed=44)
     gen_mcts("19x19x8_mid", 19, 19, 8, 1, G=3, base=2, training=True, D=8, breadth=16, root_turns=12, seed=33,
              warm_tics=[10, 18, 30])
 

@@ -110,6 +110,31 @@ def test_pit_runner_and_pit_agent():
     assert all(w in (None, 0, 1, 2, 3) for w in winners)
 
 
+@pytest.mark.parametrize("name", ["1v1", "2v2", "1v3", "3v1_7x7"])
+def test_pit_runner_against_reference(name):
+    """pit_mp_game_runner.MPGameRunner.run(Alice, Bob, Alice_snake_cnt) of the unmodified reference, recorded with two
+    stand-in value functions (tests/golden/make_golden.py gen_pit): same start layouts, the reference's food cells replayed;
+    every move of every turn and the winner list -- team split (:30-34), winner of an ended game (:44-48) and the early
+    exit when one team is gone (:49-60) -- must be identical."""
+    from alphasnake_zero_b200.utils.pit_agent import Agent as PitAgent
+    from alphasnake_zero_b200.utils.pit_mp_game_runner import MPGameRunner as PitRunner
+    from tests.helpers import KeyStubNet, load
+    from tests.test_gpu_env import init_dump
+    z = load("pit_%s.npz" % name)
+    side, S, dec, G = int(z["H"]), int(z["S"]), int(z["health_dec"]), int(z["G"])
+    acnt = None if int(z["alice_cnt"]) < 0 else int(z["alice_cnt"])
+    gr = PitRunner(side, side, S, dec, G, seed=1)
+    for gi in range(G):
+        nf = int(z["init_nfood"][gi])
+        gr.engine.set_state(gi, init_dump(side, S, z["init_start"][gi], z["init_last"][gi], z["init_food"][gi][:nf]))
+    log = []
+    winners = gr.run(PitAgent(KeyStubNet(1)), PitAgent(KeyStubNet(0)), acnt, spawn_trace=z["spawn"], move_log=log)
+    assert [-1 if w is None else w for w in winners] == z["winners"].tolist()
+    assert len(log) == z["moves"].shape[0]
+    for t, played in enumerate(log):
+        assert np.array_equal(played, z["moves"][t]), "moves differ in turn %d" % t
+
+
 def test_game_view_surface():
     from alphasnake_zero_b200.utils.mp_game_runner import MPGameRunner
     from oracle import oracle as orc

@@ -110,7 +110,28 @@ def test_native_search_across_table_compactions():
     assert n >= 2, "the run did not compact the table (%d times)" % n
 
 
-def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, table_log2):
+def test_native_search_with_compaction_inside_a_turn():
+    """Evicted entries keep their slots until a compaction.  With per-step host synchronisation (the network path) the engine
+    sees the occupancy and compacts between two epochs of one root turn when the table is more than 3/4 full; the result
+    is still the oracle's, entry for entry."""
+    n = _native_search_against_oracle(11, 4, 32, 4, 16, 2.0, True, 14, 12, sync_steps=True, want_mid=True)
+    assert n >= 2
+
+
+def test_table_overflow_is_an_error():
+    """a table too small for one root turn: probes find no slot, rows are dropped, and the turn must FAIL (ASZ_ERR_CAPACITY)
+    instead of returning moves that differ silently from the reference's"""
+    from alphasnake_zero_b200.engine import AszError
+    eng = _engine(side=11, snakes=4, games=64, seed=1, max_depth=8, max_breadth=16, softmax_base=2.0, training=True, table_log2=10)
+    eng.reset()
+    with pytest.raises(AszError, match="overflow"):
+        eng.search()
+    assert eng.search_stats()["overflow"] > 0
+    eng.search_clear()
+    eng.close()
+
+
+def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, table_log2, sync_steps=False, want_mid=False):
     import torch
     from oracle import oracle as orc
     seed = 77
@@ -126,7 +147,7 @@ def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns,
     compactions, last_occupied, last_inserts = 0, 0, 0
     for t in range(turns):
         tree = torch.full((info["epochs"], info["max_steps"], G * info["P"], S), 255, dtype=torch.uint8, device="cuda")
-        q, mv = eng.search(value_fn=None, trace=tree, trace_mode=2)
+        q, mv = eng.search(value_fn=None, trace=tree, trace_mode=2, sync_steps=sync_steps)
         q = q.cpu().numpy(); mv = mv.cpu().numpy()
         live = [g for gi, g in enumerate(games) if not done[gi]]
         if not live:
@@ -168,8 +189,12 @@ def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns,
             r0 += n
         for g_i in range(0, G, 5):
             assert_dump_equal(eng.get_state(g_i), games[g_i].dump(), "root game %d after turn %d" % (g_i, t))
+    st = eng.search_stats()
+    assert st["compactions"] == compactions or sync_steps, (st, compactions)
+    if want_mid:
+        assert st["mid_turn_compactions"] >= 1, st
     eng.close()
-    return compactions
+    return st["compactions"]
 
 
 def test_policy_functions_against_reference():
