@@ -26,7 +26,7 @@ class StepArgs(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("spawn_mode", C.c_int32), ("d_actions", C.c_void_p),
                 ("d_spawn_cells", C.c_void_p), ("d_planes", C.c_void_p), ("d_row_ids", C.c_void_p),
                 ("d_keys", C.c_void_p), ("max_rows", C.c_int32), ("d_row_count", C.c_void_p), ("d_ended", C.c_void_p),
-                ("d_rewards", C.c_void_p)]
+                ("d_rewards", C.c_void_p), ("row_base", C.c_int32)]
 
 
 class NetWeights(C.Structure):
@@ -73,8 +73,18 @@ SYMBOLS = [
     ("asz_search_root_moves", _vp, [_vp]),
     ("asz_search_stats", C.c_int, [_vp, _vp]),
     ("asz_search_table_dump", C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    ("asz_records_enable", C.c_int, [_vp, C.c_int64]),
+    ("asz_records_append", C.c_int, [_vp, _vp, _vp, _vp]),
+    ("asz_records_count", C.c_int, [_vp, _vp]),
+    ("asz_records_clear", C.c_int, [_vp]),
+    ("asz_records_gather", C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    ("asz_records_planes", _vp, [_vp]),
+    ("asz_records_values", _vp, [_vp]),
+    ("asz_records_ids", _vp, [_vp]),
+    ("asz_records_turns", _vp, [_vp]),
     ("asz_net_create", C.c_int, [C.POINTER(_vp), C.POINTER(NetWeights), _i32]),
     ("asz_net_destroy", C.c_int, [_vp]),
+    ("asz_net_update_weights", C.c_int, [_vp, C.POINTER(NetWeights), _vp]),
     ("asz_net_set_variant", C.c_int, [_vp, _i32]),
     ("asz_net_forward", C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     ("asz_net_debug_layer", C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),

@@ -18,6 +18,7 @@ bool cuda_ok(cudaError_t err, const char* what);
   } while (0)
 
 struct SearchState;   // asz_mcts.cu
+struct RecordStore;   // asz_records.cu
 
 // Every entry point that takes an engine (or a network) runs on THAT object's device, whatever device is current in the
 // calling thread ("one engine per GPU": several engines on different GPUs may live in one process).
@@ -65,6 +66,7 @@ struct asz_engine {
   unsigned long long* totals = nullptr;  // [8]
   int device_hints = 1, host_hints = 0, step_hints = 1;   // L2 policy hints of env_step_kernel (asz_env.cu)
   asz::SearchState* search = nullptr;
+  asz::RecordStore* records = nullptr;   // device-resident training records (asz_records_*)
 };
 
 namespace asz {
@@ -72,4 +74,5 @@ int gameset_alloc(GameSet& gs, int n, int pc);
 void gameset_free(GameSet& gs);
 int search_create(asz_engine* e);
 void search_destroy(asz_engine* e);
+void records_destroy(asz_engine* e);
 }  // namespace asz

@@ -36,6 +36,7 @@ struct EnvParams {
   unsigned long long* prof;   // ASZ_ENV_PROFILE builds only: per-phase cycle sums (tools/env_profile.py)
   int hints;           // 1: L2 policies (planes evict_first, game records evict_last), 0: default policy everywhere
   int device, n_sm;    // the engine's device and its multiprocessor count (grid size of the persistent kernel)
+  int row_base;        // rows of this launch are written at [row_base, row_base + n) of planes / row_ids / keys (max_rows is absolute)
 };
 
 // Phase timers for the measurement build (nvcc -DASZ_ENV_PROFILE, tools/env_profile.py); they compile to nothing otherwise.
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       if (n_rows > 0) {
         CellView<G> cv;
         warp_cell_view<G>(sb, sn, cv, s_lut);
-        row = __shfl_sync(kFull, row, 0);
+        row = __shfl_sync(kFull, row, 0) + p.row_base;
         ASZ_PROF(4);   // cell view, waiting for the row atomic
         unsigned rest = live_mask;
         while (rest) {
@@ -439,6 +440,7 @@ int asz_engine_destroy(asz_engine* e) {
   if (!e) return ASZ_OK;
   DeviceGuard guard(e->device);
   search_destroy(e);
+  records_destroy(e);
   gameset_free(e->root);
   cudaFree(e->planes); cudaFree(e->row_ids); cudaFree(e->row_count); cudaFree(e->actions); cudaFree(e->spawn_cells);
   cudaFree(e->ended); cudaFree(e->rewards); cudaFree(e->totals);
@@ -477,7 +479,8 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.G = e->cfg.games; p.S = e->cfg.snakes; p.health_dec = e->cfg.health_dec;
   p.flags = a->flags; p.spawn_mode = a->spawn_mode; p.chance_thresh = e->chance_thresh; p.seed = e->cfg.seed;
   p.actions = a->d_actions; p.spawn_cells = a->d_spawn_cells;
-  p.planes = a->d_planes; p.row_ids = a->d_row_ids; p.keys = a->d_keys; p.max_rows = a->max_rows;
+  if (a->row_base < 0 || ((a->flags & ASZ_STEP_ENCODE) && a->row_base > a->max_rows)) { set_error("row_base out of range"); return ASZ_ERR_ARG; }
+  p.planes = a->d_planes; p.row_ids = a->d_row_ids; p.keys = a->d_keys; p.max_rows = a->max_rows; p.row_base = a->row_base;
   // rows are always counted in the engine's own counter (its L2 slice is known not to be the work counter's; a caller's
   // 4-byte buffer could land anywhere) and copied to the caller's d_row_count after the launch
   p.row_count = e->row_count;

@@ -751,6 +751,7 @@ struct asz_net {
   float* head = nullptr;          // [P_tot]
   float* w1r = nullptr;           // dense1 weights on the padded raster [img_stride][128]
   int n_sm = 148;
+  int device = 0;                 // the device this network lives on (asz_net_create's current device)
   int variant = 3;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_umma_kernel, one CTA per SM),
                                   // 3 = persistent over CTA pairs (conv_umma_kernel PAIR, cta_group::2)
   __nv_bfloat16* w_pair[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -759,6 +760,19 @@ struct asz_net {
 static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st);
 
 extern "C" {
+
+// operands derived from the caller's weight arrays: dense1 on the padded raster, convolution weights split for CTA pairs
+static int net_derive(asz_net* n, cudaStream_t st) {
+  dense1_raster_kernel<<<(n->img_stride * 128 + 255) / 256, 256, 0, st>>>(n->w.dense1_w, n->real, n->pitch, n->img_stride, n->w1r);
+  if (!cuda_ok(cudaGetLastError(), "dense1_raster_kernel")) return ASZ_ERR_CUDA;
+  for (int l = 0; l < 9; ++l) {
+    const int taps = l == 0 ? 1 : 9, kc_in = l == 0 ? 4 : kKC;
+    const int total = taps * kc_in * kC;
+    pair_weight_layout_kernel<<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(n->w.w_conv[l]), n->w_pair[l], taps, kc_in);
+    if (!cuda_ok(cudaGetLastError(), "pair_weight_layout_kernel")) return ASZ_ERR_CUDA;
+  }
+  return ASZ_OK;
+}
 
 // allocations of asz_net_create; on failure the caller destroys the partially built object (cudaFree(nullptr) is a no-op)
 static int net_alloc(asz_net* n, const asz_net_weights* w, int32_t chunk_images) {
@@ -784,21 +798,18 @@ static int net_alloc(asz_net* n, const asz_net_weights* w, int32_t chunk_images)
     ASZ_CUDA(cudaGetDevice(&dev));
     ASZ_CUDA(cudaGetDeviceProperties(&prop, dev));
     n->n_sm = prop.multiProcessorCount;
+    n->device = dev;
     const char* v = getenv("ASZ_NET_VARIANT");
     if (v && v[0] >= '1' && v[0] <= '3') n->variant = v[0] - '0';
   }
   { int rc = configure_umma_kernels(); if (rc != ASZ_OK) return rc; }
   ASZ_CUDA(cudaFuncSetAttribute(dense_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   ASZ_CUDA(cudaMalloc(&n->w1r, (size_t)n->img_stride * 128 * sizeof(float)));
-  dense1_raster_kernel<<<(n->img_stride * 128 + 255) / 256, 256>>>(w->dense1_w, n->real, n->pitch, n->img_stride, n->w1r);
-  ASZ_CUDA(cudaGetLastError());
   for (int l = 0; l < 9; ++l) {
     const int taps = l == 0 ? 1 : 9, kc_in = l == 0 ? 4 : kKC;
-    const int total = taps * kc_in * kC;
-    ASZ_CUDA(cudaMalloc(&n->w_pair[l], (size_t)total * 16));
-    pair_weight_layout_kernel<<<(total + 255) / 256, 256>>>(reinterpret_cast<const __nv_bfloat16*>(w->w_conv[l]), n->w_pair[l], taps, kc_in);
-    ASZ_CUDA(cudaGetLastError());
+    ASZ_CUDA(cudaMalloc(&n->w_pair[l], (size_t)taps * kc_in * kC * 16));
   }
+  { int rc = net_derive(n, nullptr); if (rc != ASZ_OK) return rc; }
   ASZ_CUDA(cudaDeviceSynchronize());
   return ASZ_OK;
 }
@@ -815,8 +826,20 @@ int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images
   return ASZ_OK;
 }
 
+// New weights for an existing network (the per-generation weight push, alpha_snake_zero_trainer.py:52-57, 79-83): the
+// pointers of *w replace the old ones (same board side; the caller keeps the arrays alive) and the derived operands are
+// rebuilt on `stream`, ordered after whatever the caller enqueued there to fill the arrays (e.g. an NCCL broadcast).
+int asz_net_update_weights(asz_net* n, const asz_net_weights* w, void* stream) {
+  if (!n || !w) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if (w->side != n->side) { set_error("asz_net_update_weights: board side differs from the network's"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(n->device);
+  n->w = *w;
+  return net_derive(n, (cudaStream_t)stream);
+}
+
 int asz_net_destroy(asz_net* n) {
   if (!n) return ASZ_OK;
+  DeviceGuard guard(n->device);
   for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
   cudaFree(n->col); cudaFree(n->head); cudaFree(n->w1r);
   for (int l = 0; l < 9; ++l) cudaFree(n->w_pair[l]);
@@ -857,6 +880,7 @@ int asz_net_set_variant(asz_net* n, int32_t variant) {
 
 int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_values, void* stream) {
   if (!n || !d_planes || !d_values) { set_error("null argument"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(n->device);
   return net_forward_impl(n, d_planes, count, d_values, -1, nullptr, (cudaStream_t)stream);
 }
 
@@ -864,6 +888,7 @@ int asz_net_debug_layer(asz_net* n, const float* d_planes, int32_t count, int32_
   if (!n || !d_planes || !d_act) { set_error("null argument"); return ASZ_ERR_ARG; }
   if (count > n->chunk) { set_error("debug export handles one chunk"); return ASZ_ERR_ARG; }
   if (layer < 0 || layer > 8) { set_error("layer must be in 0..8"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(n->device);
   return net_forward_impl(n, d_planes, count, nullptr, layer, d_act, (cudaStream_t)stream);
 }
 

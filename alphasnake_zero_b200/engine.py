@@ -207,6 +207,46 @@ class Engine:
         order = np.lexsort((keys[:, 1], keys[:, 0]))
         return dict(keys=keys[order], W=W[order], N=N[order], Q=(W / N)[order] if n else W, age=age[order])
 
+    # ---- training records kept on the device (Agent.records / Agent.values, agent.py:21-23, 93-97) ---------------------
+    def records_enable(self, capacity_rows):
+        check(self.L.asz_records_enable(self.h, int(capacity_rows)))
+        self.records_capacity = int(capacity_rows)
+
+    def records_append(self, root_q=None):
+        """root states + root Q rows of every live snake into the device store; returns the number of records held."""
+        n = C.c_int64(0)
+        check(self.L.asz_records_append(self.h, _ptr(root_q), C.byref(n), self.stream))
+        return n.value
+
+    def records_count(self):
+        n = C.c_int64(0)
+        check(self.L.asz_records_count(self.h, C.byref(n)))
+        return n.value
+
+    def records_clear(self):
+        check(self.L.asz_records_clear(self.h))
+
+    def records_gather(self, idx, mirror=True):
+        """alpha_snake_zero_trainer.py:70-77, 93-100: (X [m, N, N, 3], V [m, 3]) device tensors, m = 2n with the mirrored copies
+        after the n originals when mirror.  idx: int64 indices (any array-like or a cuda tensor)."""
+        idx = torch.as_tensor(idx, dtype=torch.int64).to(self.device).contiguous()
+        n = idx.numel()
+        m = 2 * n if mirror else n
+        X = torch.empty(m, self.N, self.N, 3, dtype=torch.float32, device=self.device)
+        V = torch.empty(m, 3, dtype=torch.float32, device=self.device)
+        check(self.L.asz_records_gather(self.h, _ptr(idx), n, int(bool(mirror)), _ptr(X), _ptr(V), self.stream))
+        return X, V
+
+    def records_views(self):
+        """(planes [n, N, N, 3], values [n, 3], ids [n] int32 = game*8 + snake, turns [n] int32) views of the store"""
+        n = max(self.records_count(), 1)       # the store may have grown: wrap what is filled, not a remembered capacity
+        pl = self._wrap(self.L.asz_records_planes(self.h), (n, self.N, self.N, 3), torch.float32)
+        va = self._wrap(self.L.asz_records_values(self.h), (n, 3), torch.float32)
+        ids = self._wrap(self.L.asz_records_ids(self.h), (n,), torch.int32)
+        tu = self._wrap(self.L.asz_records_turns(self.h), (n,), torch.int32)
+        n = self.records_count()
+        return pl[:n], va[:n], ids[:n], tu[:n]
+
     # ---- helpers for the drop-in classes ---------------------------------------------------------------------------
     def alive_mask(self):
         """bool [G, S] (device): snake alive and game not finished."""

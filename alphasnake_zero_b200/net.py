@@ -41,6 +41,17 @@ class NativeNet:
         self.L = _lib.lib()
         self.side = int(weights["side"])
         self.N = 2 * self.side - 1
+        self._keep, self._nw = self._upload(weights)
+        nw = self._nw
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.L.asz_net_create(C.byref(h), C.byref(nw), chunk_images))
+        self.h = h
+        if variant is not None:
+            check(self.L.asz_net_set_variant(self.h, int(variant)))
+
+    def _upload(self, weights):
+        """device copies of the weights in the layouts the kernels consume -> (tensors kept alive, asz_net_weights)"""
         dev = self.device
         keep = []
 
@@ -66,13 +77,17 @@ class NativeNet:
         nw.dense1_b = up(weights["dense1_b"].astype(np.float32), torch.float32)
         nw.dense2_w = up(weights["dense2_w"].astype(np.float32), torch.float32)
         nw.dense2_b = up(weights["dense2_b"].astype(np.float32), torch.float32)
+        return keep, nw
+
+    def update(self, weights):
+        """new weights for the same network object (per-generation weight push): asz_net_update_weights"""
+        assert int(weights["side"]) == self.side
+        keep, nw = self._upload(weights)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(self.L.asz_net_update_weights(self.h, C.byref(nw), st))
+            torch.cuda.current_stream(self.device).synchronize()      # the old arrays may be freed once nothing reads them
         self._keep, self._nw = keep, nw
-        h = C.c_void_p()
-        with torch.cuda.device(dev):
-            check(self.L.asz_net_create(C.byref(h), C.byref(nw), chunk_images))
-        self.h = h
-        if variant is not None:
-            check(self.L.asz_net_set_variant(self.h, int(variant)))
 
     def __del__(self):
         try:

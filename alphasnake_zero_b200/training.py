@@ -1,6 +1,6 @@
 """Weight update for AlphaNNet.train (alpha_nnet.py:58-59, 78-106) -- OUTSIDE the self-play hot path.
 Plain PyTorch autograd over the same weight dictionary: MSE + l2(1e-5) on every kernel, Adam with the reference's
-piecewise-constant schedule (x0.25 every 20 optimizer steps, 0 after step 100), batch-norm in training mode."""
+piecewise-constant schedule (x0.25 after optimizer steps 20, 40, 60, 80; 0 after step 100: Keras `step <= boundary`), batch-norm in training mode."""
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -11,11 +11,24 @@ L2 = 1e-5
 BN_MOMENTUM = 0.99   # Keras default
 
 
+def lr_at(step, lr):
+    """alpha_nnet.py:79-84,92: Keras PiecewiseConstantDecay(boundaries=[20, 40, 60, 80, 100], values=[lr, lr/4, ..., lr/256, 0])
+    evaluated at the optimizer's iteration counter (0 for the first update): values[0] while step <= 20, values[i] while
+    boundaries[i-1] < step <= boundaries[i], 0 after step 100."""
+    if step > 100:
+        return 0.0
+    return lr * 0.25 ** (max(step - 1, 0) // 20)
+
+
 def fit(net, X, Y, epochs, batch_size, lr):
     dev = net.device
     w = net.weights
-    X = torch.from_numpy(np.ascontiguousarray(np.array(X, dtype=np.float32))).to(dev).permute(0, 3, 1, 2).contiguous()
-    Y = torch.from_numpy(np.ascontiguousarray(np.array(Y, dtype=np.float32))).to(dev)
+    def dev_tensor(a):      # device tensors (the engine's record gather) are used as they are; lists / arrays are uploaded once
+        if torch.is_tensor(a):
+            return a.to(dev, torch.float32)
+        return torch.from_numpy(np.ascontiguousarray(np.array(a, dtype=np.float32))).to(dev)
+    X = dev_tensor(X).permute(0, 3, 1, 2).contiguous()
+    Y = dev_tensor(Y)
     P, bn_names, kernels = {}, [], []
     for k, v in w.items():
         if isinstance(v, dict):
@@ -55,7 +68,7 @@ def fit(net, X, Y, epochs, batch_size, lr):
         perm = torch.randperm(n, device=dev)
         for i in range(0, n, batch_size):
             idx = perm[i:i + batch_size]
-            sched = lr * (0.25 ** (step // 20)) if step < 100 else 0.0     # alpha_nnet.py:79-84
+            sched = lr_at(step, lr)
             for g in opt.param_groups:
                 g["lr"] = sched
             loss = F.mse_loss(forward(X[idx]), Y[idx]) + L2 * sum((P[k] ** 2).sum() for k in kernels)

@@ -145,6 +145,14 @@ class AlphaNNet:
             self._native = NativeNet(self.weights, self.device)
         return self._native
 
+    def set_weights(self, weights):
+        """replace the weight dictionary and refresh every device copy `v` uses (the native network's operands through
+        asz_net_update_weights, the PyTorch parameters by rebuilding them): the per-generation weight push"""
+        self.weights = weights
+        self._torch = None
+        if self._native is not None:
+            self._native.update(weights)
+
     def _forward_host(self, X):
         X = np.ascontiguousarray(np.array(X, dtype=np.float32))
         out = []

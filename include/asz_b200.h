@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define ASZ_MAX_SNAKES 8
-#define ASZ_VERSION 1
+#define ASZ_VERSION 2
 
 typedef enum {
   ASZ_OK = 0,
@@ -104,6 +104,8 @@ typedef struct {
   int32_t* d_row_count;          /* [1] number of rows written by this call (the call zeroes it first) */
   uint8_t* d_ended;              /* [G] 1 when the game ended in this tic (may be NULL) */
   int8_t* d_rewards;             /* [G*8] final rewards of games that ended in this tic: 0 none, 1, -1 (may be NULL) */
+  int32_t row_base;              /* rows are written at [row_base, row_base + n) of d_planes / d_row_ids / d_keys; max_rows
+                                    stays the absolute capacity (rows past it are dropped, *d_row_count still counts them) */
 } asz_step_args;
 
 /* Enqueues one fused launch.  Row order inside d_planes is unspecified across games (rows of one game are
@@ -199,6 +201,30 @@ int asz_search_stats(asz_engine* e, uint64_t* h_stats);
 int asz_search_table_dump(asz_engine* e, int32_t cap, uint64_t* h_keys, float* h_w, float* h_n, int32_t* h_age,
                           int32_t* h_count);
 
+/* ---- training records: Agent.records / Agent.values (agent.py:21-23, 93-97) kept in HBM, and the trainer's sample +
+ * mirror augmentation (alpha_snake_zero_trainer.py:62-77, 93-100) as one gather kernel ------------------------------
+ * The reference appends one (root state, root Q) pair per live snake per root turn to two host lists; here the root
+ * planes are encoded straight into an engine-owned store and only the moves go to the host each turn. */
+/* allocates room for capacity_rows records (plane + 3 values + id + turn each); an earlier store is dropped.  The store
+ * doubles when an append might not fit (device pointers from the accessors below change then). */
+int asz_records_enable(asz_engine* e, int64_t capacity_rows);
+/* agent.py:93-97 after asz_search_finish: state of every live snake of every live root game + its root Q row
+ * (d_root_q [games*8][3], NULL = the engine's root Q buffer).  Records of one call are contiguous, rows of a game
+ * contiguous in ascending snake id, game order unspecified (asz_records_ids tells).  Synchronises the stream;
+ * *h_count = records held afterwards; ASZ_ERR_CAPACITY when the store cannot grow (nothing is dropped silently). */
+int asz_records_append(asz_engine* e, const float* d_root_q, int64_t* h_count, void* stream);
+int asz_records_count(asz_engine* e, int64_t* h_count);
+/* Agent.clear (agent.py:140-147) for the records */
+int asz_records_clear(asz_engine* e);
+/* alpha_snake_zero_trainer.py:70-77: X = records[idx], V = values[idx]; with mirror != 0 the flipped copies
+ * (states flipped along the width axis, values reversed: :93-100) follow the n originals.  d_idx [n] int64 DEVICE
+ * indices (the reference draws them with random.sample on the host); d_X [(mirror ? 2 : 1) * n][plane], d_V [..][3]. */
+int asz_records_gather(asz_engine* e, const int64_t* d_idx, int32_t n, int32_t mirror, float* d_X, float* d_V, void* stream);
+float* asz_records_planes(asz_engine* e);     /* device [capacity][plane] */
+float* asz_records_values(asz_engine* e);     /* device [capacity][3] */
+int32_t* asz_records_ids(asz_engine* e);      /* device [capacity] game*8 + snake */
+int32_t* asz_records_turns(asz_engine* e);    /* device [capacity] index of the append call */
+
 /* ---- value network: AlphaNNet.v_net.predict (alpha_nnet.py:19-56, 62), inference only --------------------------
  * Weights are passed as DEVICE pointers in the layouts the kernels consume (alphasnake_zero_b200/net.py builds them
  * from the Keras-layout arrays: conv kernels HWIO, dense (in, out), BN gamma/beta/moving mean/variance, eps 1e-3):
@@ -225,6 +251,9 @@ typedef struct asz_net asz_net;
 /* chunk_images: images processed per pass (sizes the activation workspace: ~31 KB... 124 KB per image and buffer) */
 int asz_net_create(asz_net** out, const asz_net_weights* w, int32_t chunk_images);
 int asz_net_destroy(asz_net* net);
+/* the per-generation weight push (alpha_snake_zero_trainer.py:52-57, 79-83): *w replaces the network's weight pointers
+ * (same side; arrays stay owned by the caller) and the operands derived from them are rebuilt on `stream` */
+int asz_net_update_weights(asz_net* net, const asz_net_weights* w, void* stream);
 /* convolution kernel variant: 1 = one tile per CTA, 2 = persistent single-CTA, 3 = persistent CTA pairs (cta_group::2).
  * 2 and 3 compute the same bits (same accumulation order), 1 agrees to bf16 rounding; the default is 3, the fastest
  * (environment override: ASZ_NET_VARIANT). */

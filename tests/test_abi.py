@@ -29,7 +29,7 @@ def test_header_symbols_exported():
 def test_version_and_error_string():
     from alphasnake_zero_b200 import _lib
     L = _lib.lib()
-    assert L.asz_version() == 1
+    assert L.asz_version() == 2
     assert isinstance(L.asz_last_error(), bytes)
 
 

@@ -103,3 +103,44 @@ def test_conv_variants_agree(side, S, n, chunk):
         assert np.array_equal(acts[3].view(np.uint32), acts[2].view(np.uint32)), layer
         # different accumulation order => different bf16 roundings, which compound over the layers
         assert np.abs(acts[1] - acts[2]).max() <= 0.03 * np.abs(acts[2]).max() + 1e-3, layer
+
+
+def test_weight_update_equals_a_fresh_network():
+    """asz_net_update_weights (the per-generation weight push): after AlphaNNet.set_weights the SAME native network object gives
+    bit-identical outputs to a network created from the new weights, and differs from the old ones"""
+    import torch
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet, init_weights
+    X = torch.from_numpy(game_planes(11, 4, 300, seed=9)).cuda()
+    a = AlphaNNet(input_shape=(21, 21, 3), seed=1)
+    old = a.v_device(X).clone()
+    nat = a._get_native()
+    w2 = init_weights((21, 21, 3), seed=2)
+    a.set_weights(w2)
+    assert a._get_native() is nat                       # same object, new operands
+    new = a.v_device(X).clone()
+    fresh = AlphaNNet(input_shape=(21, 21, 3), seed=2).v_device(X)
+    assert torch.equal(new, fresh) and not torch.equal(new, old)
+
+
+def test_parallel_collectives_on_nccl():
+    """parallel.py over the nccl backend (world size 1 on this box; the 8-GPU bench leg runs the same calls): device tensors
+    for every collective, weights pushed into the live native network"""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from alphasnake_zero_b200 import parallel
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+    try:
+        net = AlphaNNet(input_shape=(21, 21, 3), seed=5)
+        net._get_native()
+        parallel.broadcast_weights(net, src=0)
+        assert parallel.weights_equal_all_ranks(net.weights)
+        assert parallel.reduce_counters([4.0, 2.0, 0, 0, 6.0, 20.0], 2, dst=0) == [2.0, 1.0, 0.0, 0.0, 3.0, 10.0]
+        planes = torch.rand(50, 21, 21, 3, device="cuda"); values = torch.rand(50, 3, device="cuda")
+        X, V, bs = parallel.gather_sampled_batch(50, lambda idx: (planes[idx.cuda()], values[idx.cuda()]), (21, 21, 3), batch_size=16,
+                                                 max_batches=2, dst=0)
+        assert X.shape == (32, 21, 21, 3) and V.shape == (32, 3) and bs == 16 and X.is_cuda
+    finally:
+        dist.destroy_process_group()
