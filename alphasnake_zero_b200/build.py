@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(cc, srcs))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcuda"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcuda", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)

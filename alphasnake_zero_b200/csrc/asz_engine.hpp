@@ -1,6 +1,7 @@
 // asz_engine.hpp -- host-side engine object behind the C ABI (include/asz_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <string>
@@ -31,6 +32,14 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
   DeviceGuard(const DeviceGuard&) = delete;
   DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// NVTX range per phase (tic / encode, probe, net, sample, finish, records): visible in Nsight Systems / ncu --nvtx, a
+// no-op function-pointer check when no tool is attached (tracing row)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 constexpr int kMaxDevices = 64;   // per-device "kernel attributes configured" flags (function attributes are per device)
 

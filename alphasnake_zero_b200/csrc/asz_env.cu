@@ -472,6 +472,7 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   if ((a->flags & ASZ_STEP_TIC) && a->spawn_mode == ASZ_SPAWN_REPLAY && !a->d_spawn_cells) { set_error("d_spawn_cells is null"); return ASZ_ERR_ARG; }
   if (a->spawn_mode < 0 || a->spawn_mode > 2) { set_error("bad spawn_mode"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:env_step (tic + encode)");
   cudaStream_t st = (cudaStream_t)stream;
   EnvParams p;
   p.device = e->device; p.n_sm = e->n_sm;
@@ -505,6 +506,7 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
                       float* h_planes, int32_t* h_row_ids, void* stream) {
   if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:env_step_host");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t G = (size_t)e->cfg.games;
   if ((flags & ASZ_STEP_TIC) && !(flags & ASZ_STEP_RANDOM_ACT)) {

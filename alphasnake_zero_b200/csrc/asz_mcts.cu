@@ -647,6 +647,7 @@ int asz_search_begin(asz_engine* e, void* stream) {
 int asz_search_epoch_begin(asz_engine* e, void* stream) {
   if (!e || !e->search || !e->search->open) { set_error("no open search"); return ASZ_ERR_STATE; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:search epoch_begin (subgame x8)");
   SearchState* s = e->search;
   if (s->epoch + 1 >= s->E) { set_error("all epochs of this root turn are done"); return ASZ_ERR_STATE; }
   s->epoch += 1; s->step = 0;
@@ -673,6 +674,7 @@ int asz_search_epoch_begin(asz_engine* e, void* stream) {
 int asz_search_step_probe(asz_engine* e, int32_t* h_n_miss, void* stream) {
   if (!e || !e->search || !e->search->open || e->search->epoch < 0) { set_error("no open epoch"); return ASZ_ERR_STATE; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:search step_probe (tic, backup, key, probe)");
   SearchState* s = e->search;
   if (s->step > s->Dmax) { set_error("epoch already finished"); return ASZ_ERR_STATE; }
   s->step += 1;
@@ -698,6 +700,7 @@ int asz_search_step_probe(asz_engine* e, int32_t* h_n_miss, void* stream) {
 int asz_search_step_sample(asz_engine* e, const float* d_values, uint8_t* d_trace, int32_t trace_mode, void* stream) {
   if (!e || !e->search || !e->search->open || e->search->step < 1) { set_error("no probed step"); return ASZ_ERR_STATE; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:search step_sample (priors, softermax, sample)");
   SearchState* s = e->search;
   if (s->step > s->Dmax) return ASZ_OK;   // the closing probe of an epoch has no rows
   if (trace_mode != 0 && !d_trace) { set_error("trace_mode set but d_trace is null"); return ASZ_ERR_ARG; }
@@ -722,6 +725,7 @@ int asz_search_stub_values(asz_engine* e, void* stream) {
 int asz_obstacle_mask(asz_engine* e, const float* d_planes, int32_t n, float* d_values, void* stream) {
   if (!e || !d_planes || !d_values) { set_error("null argument"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:obstacle_mask");
   if (n <= 0) return ASZ_OK;
   obstacle_mask_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_planes, n, e->cfg.side, e->cfg.numpy1_mask, d_values);
   return cuda_ok(cudaGetLastError(), "obstacle_mask_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
@@ -738,6 +742,7 @@ int asz_debug_policy(const float* d_z, const double* d_u, int32_t n, float base,
 int asz_search_finish(asz_engine* e, const uint8_t* d_root_trace, float* d_root_q, uint8_t* d_root_moves, void* stream) {
   if (!e || !e->search || !e->search->open) { set_error("no open search"); return ASZ_ERR_STATE; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:search finish (root Q, moves, eviction)");
   SearchState* s = e->search;
   cudaStream_t st = (cudaStream_t)stream;
   SearchParams p = make_params(e);

@@ -881,6 +881,7 @@ int asz_net_set_variant(asz_net* n, int32_t variant) {
 int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_values, void* stream) {
   if (!n || !d_planes || !d_values) { set_error("null argument"); return ASZ_ERR_ARG; }
   DeviceGuard guard(n->device);
+  NvtxRange nvtx("asz:net forward");
   return net_forward_impl(n, d_planes, count, d_values, -1, nullptr, (cudaStream_t)stream);
 }
 

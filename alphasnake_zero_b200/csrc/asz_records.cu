@@ -130,6 +130,7 @@ int asz_records_enable(asz_engine* e, int64_t capacity_rows) {
 int asz_records_append(asz_engine* e, const float* d_root_q, int64_t* h_count, void* stream) {
   if (!e || !e->records) { set_error("asz_records_append: records are not enabled"); return ASZ_ERR_STATE; }
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:records append");
   RecordStore* r = e->records;
   cudaStream_t st = (cudaStream_t)stream;
   const float* q = d_root_q ? d_root_q : asz_search_root_q(e);
@@ -190,6 +191,7 @@ int asz_records_gather(asz_engine* e, const int64_t* d_idx, int32_t n, int32_t m
   if (!d_idx || !d_X || !d_V || n < 0) { set_error("asz_records_gather: bad argument"); return ASZ_ERR_ARG; }
   if (n == 0) return ASZ_OK;
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:records gather + mirror");
   RecordStore* r = e->records;
   records_gather_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(r->planes, r->values, d_idx, n, 2 * e->cfg.side - 1, mirror ? 1 : 0, r->count,
                                                             d_X, d_V);

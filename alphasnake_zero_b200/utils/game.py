@@ -13,15 +13,83 @@ class Snake:
 
 
 class Game:
+    """Two ways to get one:
+      * `Game(engine, i)`: a view of game i of a multi-game Engine (what MPGameRunner.games holds);
+      * `Game(ID, height, width, snake_cnt, health_dec=1, food_spawn_chance=0.15)`: the reference's own constructor
+        (game.py:13): a standalone game backed by a private one-game Engine, for callers that step a game by hand.
+    `tic` and `subgame` (game.py:87, 266) work on both; on a view `tic` steps only that game (through a one-game scratch
+    engine), which is a convenience path -- lockstep work belongs to the runners."""
 
-    def __init__(self, engine, ID):
-        self.engine = engine
-        self.id = ID
-        self.height = self.width = engine.side
-        self.snake_cnt = engine.S
+    def __init__(self, engine_or_id, ID_or_height=None, width=None, snake_cnt=4, health_dec=1, food_spawn_chance=0.15, seed=None):
+        from ..engine import Engine
+        if isinstance(engine_or_id, Engine):
+            self.engine, self.id, self._index, self._own = engine_or_id, ID_or_height, ID_or_height, False
+        else:
+            height = ID_or_height
+            if height != width:
+                raise ValueError("boards must be square (rot90 of the plane, game.py:257)")
+            self.id, self._index, self._own = engine_or_id, 0, True
+            self.engine = Engine(side=height, snakes=snake_cnt, health_dec=health_dec, food_chance=food_spawn_chance, games=1,
+                                 seed=int(engine_or_id) if seed is None else seed)
+            self.engine.reset()
+        self.height = self.width = self.engine.side
+        self.snake_cnt = self.engine.S
+        self.health_dec = self.engine.cfg.health_dec
+        self.food_spawn_chance = float(self.engine.cfg.food_chance)
+
+    # ---- game.py:87-205 -------------------------------------------------------------------------------------------
+    def tic(self, moves, show=False):
+        """moves[i] in {0, 1, 2} for the i-th LIVE snake (ascending id).  Returns 0, or the rewards list when the game ended."""
+        import torch
+        from .. import _lib
+        d = self._dump()
+        live = [s for s in range(self.snake_cnt) if d["snake"][s][0]]
+        if len(moves) != len(live):
+            raise ValueError("tic needs one move per live snake (%d), got %d" % (len(live), len(moves)))
+        eng, idx = self.engine, self._index
+        if not self._own and eng.G > 1:
+            eng, idx = self._scratch(), 0
+            eng.set_state(0, d, episode=int(d["counters"][6]))
+        actions = np.ones((eng.G, 8), np.uint8)
+        for s, m in zip(live, moves):
+            actions[idx, s] = int(m)
+        eng.step(actions=torch.from_numpy(actions).to(eng.device), spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=False)
+        after = eng.get_state(idx)
+        if show:                                           # game.py:140-141,194-195: two frames per tic into replay.rep
+            with open("replay.rep", "a") as f:
+                f.write(frames_text(replay_frames(d, list(moves), after, self.width)))
+        if eng is not self.engine:
+            self.engine.set_state(self._index, after, episode=int(after["counters"][6]))
+            if int(after["counters"][7]):
+                self._finish_in_parent(after)
+        if int(after["counters"][7]):
+            return [None if r == 0 else float(r) for r in after["snake"][:, 5]]
+        return 0
+
+    def _scratch(self):
+        """one-game engine with this game's rules, shared by all views of the same parent engine"""
+        from ..engine import Engine
+        p = self.engine
+        if getattr(p, "_scratch_engine", None) is None:
+            p._scratch_engine = Engine(side=p.side, snakes=p.S, health_dec=p.cfg.health_dec, food_chance=float(p.cfg.food_chance),
+                                       games=1, seed=int(p.cfg.seed) ^ 0x5ca7c4, device=p.device)
+        return p._scratch_engine
+
+    def _finish_in_parent(self, after):
+        # asz_set_state marks a game with <= 1 live snake as finished, which is exactly an ended game; nothing else to do
+        return None
+
+    # ---- game.py:266-276 ------------------------------------------------------------------------------------------
+    def subgame(self, ID):
+        """a standalone copy that never spawns food (food_spawn_chance 0.0), counters restarted, rewards kept"""
+        d = self._dump()
+        g = Game(ID, self.height, self.width, self.snake_cnt, self.health_dec, 0.0)
+        c = np.zeros(8, np.int32)
+        g.engine.set_state(0, dict(snake=d["snake"], owner=d["owner"], dist=d["dist"], food=d["food"], counters=c))
+        return g
 
     def _dump(self):
-        return self.engine.get_state(self.id)
+        return self.engine.get_state(self._index)
 
     @property
     def snakes(self):
@@ -67,7 +135,7 @@ class Game:
 
     def get_states(self):
         """game.py:68-69: planes of the live snakes, in live-list order (encode kernel, copied to the host)."""
-        return self.engine.states_of(self.id)
+        return self.engine.states_of(self._index)
 
 
 # ---- replay.rep (game.py:140-141, 194-195, 281-300; read by player.py:63-79) -----------------------------------------

@@ -1,4 +1,5 @@
-"""smoke(): one small search + value-network invocation on cuda:0, checked against the CPU oracle."""
+"""__graft_entry__.smoke(): one small search + value-network invocation on cuda:0, checked against the CPU oracle.
+Lives under tests/ because it imports oracle/ (the product package never does)."""
 import numpy as np
 import torch
 
@@ -6,8 +7,8 @@ import torch
 def run():
     from oracle import net_oracle as no
     from oracle import oracle as orc
-    from .engine import Engine
-    from .net import NativeNet
+    from alphasnake_zero_b200.engine import Engine
+    from alphasnake_zero_b200.net import NativeNet
     G, S, D, B, seed = 8, 4, 8, 16, 11
     eng = Engine(side=11, snakes=S, games=G, seed=seed, max_depth=D, max_breadth=B, softmax_base=2.0, training=True,
                  table_log2=18)

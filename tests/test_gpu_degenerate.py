@@ -73,15 +73,26 @@ def test_plane_batch_smaller_than_the_live_rows():
     eng.close()
 
 
-def test_table_overflow_is_counted_not_fatal():
+def test_table_overflow_fails_the_turn_but_not_the_engine():
+    """a table far too small: the turn fails with ASZ_ERR_CAPACITY (a dropped row would play an arbitrary move), the counters say
+    why, the outputs that were written are well formed, and the engine keeps working after Agent.clear"""
+    from alphasnake_zero_b200.engine import AszError
     eng = _engine(side=11, snakes=4, games=64, seed=2, max_depth=8, max_breadth=32, softmax_base=2.0, training=True, table_log2=10)
     eng.reset()
-    q, mv = eng.search(value_fn=None)
+    with pytest.raises(AszError, match="overflow"):
+        eng.search(value_fn=None)
     st = eng.search_stats()
     assert st["overflow"] > 0 and st["evals"] > 0
-    mvh = mv.cpu().numpy()
-    assert set(np.unique(mvh)) <= {0, 1, 2, 255} and np.isfinite(q.cpu().numpy()).all()
+    q = eng._wrap(eng.L.asz_search_root_q(eng.h), (64, 8, 3), torch_float32())
+    assert np.isfinite(q.cpu().numpy()).all()
+    eng.search_clear()
+    assert eng.search_stats()["overflow"] == 0
     eng.close()
+
+
+def torch_float32():
+    import torch
+    return torch.float32
 
 
 def test_argument_errors_are_reported():

@@ -150,6 +150,60 @@ def test_game_view_surface():
     assert len(g.food) >= 2
 
 
+def test_game_seam_ctor_tic_subgame():
+    """SURVEY 8(b) last row: Game(ID, height, width, snake_cnt, health_dec, food_spawn_chance), .tic(moves), .subgame(ID)
+    (game.py:13, 87, 266) for callers that step one game by hand -- standalone games and views of a runner's games"""
+    from alphasnake_zero_b200.utils.game import Game
+    from alphasnake_zero_b200.utils.mp_game_runner import MPGameRunner
+    from oracle import oracle as orc
+    from tests.helpers import assert_dump_equal
+    rng = np.random.default_rng(3)
+    g = Game(7, 11, 11, 4, 1, 0.15)
+    og = orc.OracleGame(11, 11, 4, 1); og.init_native(7, 0, 0)
+    assert g.height == 11 and g.snake_cnt == 4 and g.rewards == [None] * 4 and len(g.snakes) == 4
+    sub_checked = False
+    for t in range(200):
+        mv = rng.integers(0, 3, size=og.n_live).tolist()
+        if t == 3:
+            sg, osg = g.subgame(99), og.clone()               # never spawns food, counters restart, state copied
+            assert sg.id == 99 and sg.food_spawn_chance == 0.0 and sg.food == g.food
+            for _ in range(4):
+                m2 = rng.integers(0, 3, size=osg.n_live).tolist()
+                r2 = sg.tic(m2)
+                e2 = osg.tic(np.array(m2, np.int32), spawn_mode=0)
+                got, want = sg._dump(), osg.dump()
+                for k in ("owner", "dist", "food"):
+                    assert np.array_equal(got[k], want[k])
+                assert np.array_equal(got["snake"][:, :3], want["snake"][:, :3])
+                assert (r2 != 0) == bool(e2)
+                if e2:
+                    break
+            assert_dump_equal(g._dump(), og.dump(), "the root game is untouched by its sub-game")
+            sub_checked = True
+        res = g.tic(mv)
+        ended = og.tic(np.array(mv, np.int32), spawn_mode=2, chance=0.15, seed=7)
+        assert_dump_equal(g._dump(), og.dump(), "standalone game tic %d" % t)
+        if ended:
+            want = [None if r == 0 else float(r) for r in og.dump()["snake"][:, 5]]
+            assert res == want and res.count(1.0) <= 1
+            break
+        assert res == 0
+    assert sub_checked and ended
+    with pytest.raises(ValueError):
+        Game(1, 11, 11, 4).tic([1, 1])                        # one move per live snake
+    # a view of a runner's game: tic steps that game only
+    gr = MPGameRunner(11, 11, 4, 1, 5, seed=9, verbose=False)
+    gr._make_engine(RandomAgent(0))
+    before = [gr.engine.get_state(i) for i in range(5)]
+    assert gr.games[2].tic([1, 1, 1, 1]) == 0
+    for i in (0, 1, 3, 4):
+        assert_dump_equal(gr.engine.get_state(i), before[i], "game %d must not move" % i)
+    o2 = orc.OracleGame(11, 11, 4, 1); o2.load_dump(before[2])
+    o2.tic(np.array([1, 1, 1, 1], np.int32), spawn_mode=0)
+    got = gr.engine.get_state(2)
+    assert np.array_equal(got["snake"][:, :5], o2.dump()["snake"][:, :5]) and got["counters"][5] == 1
+
+
 def test_single_game_writes_replay_rep(tmp_path, monkeypatch):
     """test_model.py:13-23: one game with the search agent, replay.rep gets two frames per tic (game.py:140-141,194-195) in
     the text format player.py:63-79 parses"""

@@ -118,19 +118,6 @@ def test_native_search_with_compaction_inside_a_turn():
     assert n >= 2
 
 
-def test_table_overflow_is_an_error():
-    """a table too small for one root turn: probes find no slot, rows are dropped, and the turn must FAIL (ASZ_ERR_CAPACITY)
-    instead of returning moves that differ silently from the reference's"""
-    from alphasnake_zero_b200.engine import AszError
-    eng = _engine(side=11, snakes=4, games=64, seed=1, max_depth=8, max_breadth=16, softmax_base=2.0, training=True, table_log2=10)
-    eng.reset()
-    with pytest.raises(AszError, match="overflow"):
-        eng.search()
-    assert eng.search_stats()["overflow"] > 0
-    eng.search_clear()
-    eng.close()
-
-
 def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, table_log2, sync_steps=False, want_mid=False):
     import torch
     from oracle import oracle as orc
