@@ -26,7 +26,9 @@ class Engine:
                  softmax_base=100.0, training=False, table_log2=0, numpy1_mask=False, device=None):
         if not torch.cuda.is_available():
             raise AszError("no CUDA device: alphasnake_zero_b200 has no CPU fallback")
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        if isinstance(device, torch.device):
+            device = device.index
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.L = _lib.lib()
         self.side, self.S, self.G = side, snakes, games
         self.N = 2 * side - 1

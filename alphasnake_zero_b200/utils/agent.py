@@ -33,6 +33,17 @@ class DeviceRecords:
     def __iter__(self):
         return (self[i] for i in range(len(self)))
 
+    def __eq__(self, other):
+        """list semantics for callers that compare with a list (e.g. `agent.records == []` after clear())"""
+        try:
+            if len(other) != len(self):
+                return False
+        except TypeError:
+            return NotImplemented
+        return all(np.array_equal(a, b) for a, b in zip(self, other))
+
+    __hash__ = None
+
 
 class Agent:
 

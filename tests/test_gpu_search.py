@@ -177,7 +177,7 @@ def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns,
         for g_i in range(0, G, 5):
             assert_dump_equal(eng.get_state(g_i), games[g_i].dump(), "root game %d after turn %d" % (g_i, t))
     st = eng.search_stats()
-    assert st["compactions"] == compactions or sync_steps, (st, compactions)
+    assert st["compactions"] >= compactions, (st, compactions)
     if want_mid:
         assert st["mid_turn_compactions"] >= 1, st
     eng.close()
