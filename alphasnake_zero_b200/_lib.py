@@ -26,7 +26,7 @@ class StepArgs(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("spawn_mode", C.c_int32), ("d_actions", C.c_void_p),
                 ("d_spawn_cells", C.c_void_p), ("d_planes", C.c_void_p), ("d_row_ids", C.c_void_p),
                 ("d_keys", C.c_void_p), ("max_rows", C.c_int32), ("d_row_count", C.c_void_p), ("d_ended", C.c_void_p),
-                ("d_rewards", C.c_void_p), ("row_base", C.c_int32)]
+                ("d_rewards", C.c_void_p), ("row_base", C.c_int32), ("plane_pitch", C.c_int32)]
 
 
 class NetWeights(C.Structure):
@@ -55,6 +55,7 @@ SYMBOLS = [
     ("asz_internal_planes", _vp, [_vp]),
     ("asz_internal_row_ids", _vp, [_vp]),
     ("asz_plane_floats", C.c_size_t, [_vp]),
+    ("asz_plane_pitch", C.c_size_t, [_vp]),
     ("asz_search_begin", C.c_int, [_vp, _vp]),
     ("asz_search_epoch_begin", C.c_int, [_vp, _vp]),
     ("asz_search_step_probe", C.c_int, [_vp, _vp, _vp]),
@@ -87,6 +88,7 @@ SYMBOLS = [
     ("asz_net_update_weights", C.c_int, [_vp, C.POINTER(NetWeights), _vp]),
     ("asz_net_set_variant", C.c_int, [_vp, _i32]),
     ("asz_net_forward", C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    ("asz_net_forward_pitched", C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     ("asz_net_debug_layer", C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
 ]
 

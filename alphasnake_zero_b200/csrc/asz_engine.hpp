@@ -62,10 +62,11 @@ struct asz_engine {
   int n_sm = 0;          // multiprocessors of `device`
   int pc = 0;            // padded cells per game
   int plane = 0;         // floats per plane
+  int pitch = 0;         // floats between consecutive planes of the engine's own buffers (plane rounded up to 8: 32-byte rows)
   uint32_t chance_thresh = 0;
   asz::GameSet root;
   // env-step scratch owned by the engine
-  float* planes = nullptr;        // [G*S][plane]
+  float* planes = nullptr;        // [G*S][pitch]
   int32_t* row_ids = nullptr;     // [G*S]
   int32_t* row_count = nullptr;   // [1]
   uint8_t* actions = nullptr;     // [G*8]

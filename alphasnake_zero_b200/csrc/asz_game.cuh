@@ -503,4 +503,116 @@ __device__ __forceinline__ void warp_encode_v2(const CellView<G>& cv, const Snak
   for (int q = 0; q < CPL; ++q) { const int t = ctx.prev_cur[q]; ctx.prev_cur[q] = ctx.prev_oth[q]; ctx.prev_oth[q] = t; }
 }
 
+// ---- plane encode, v3: pitched planes, one emission per game -------------------------------------------------------
+// The engine's own plane buffers (the network's input batch, the record store) keep consecutive planes PITCH floats apart,
+// PITCH = PLANE rounded up to 8 floats (5,312 B instead of 5,292 B at 11x11): every plane then starts on a 32-byte sector of
+// HBM, which removes everything the 4-byte alignment of dense planes costs in v2 (per-plane edge floats stored by single
+// lanes, alignment arithmetic, three separate copies per plane).  The planes of one game are consecutive rows, so the game
+// is emitted as ONE sequence of bulk copies: wall before the first window, then per plane its window (from the staging
+// buffer) and the wall run up to the next window -- the wall after plane k and the wall before plane k+1 are one contiguous
+// range, copied from a per-CTA constant "seam" buffer that holds a plane end, the pad floats and a plane start.
+// Dense planes (a caller's own [rows][N][N][3] tensor) still go through v2.
+template <class G>
+struct PitchGeo {
+  static constexpr int PITCH = ((G::PLANE + 7) / 8) * 8;
+  static constexpr int WIN = G::SIDE * 3 * G::N;                       // floats of the window rows
+  static constexpr int MAX_OFF = 15;                                   // largest staging offset of stage_off()
+  static constexpr int WSTAGE = ((MAX_OFF + WIN + 8 + 3) / 4) * 4;     // staging floats per buffer
+  static constexpr int HEAD_MAX = ((G::SIDE - 1) * 3 * G::N) & ~7;     // longest wall before a window (window on the last rows)
+  static constexpr int TAIL_MAX = PITCH - ((WIN + 7) & ~7);            // longest wall + pad after a window (window on the first rows)
+  static constexpr int SEAM_AT = (TAIL_MAX + 7) & ~7;                  // index of the plane boundary inside the seam buffer
+  static constexpr int SEAMLEN = SEAM_AT + ((HEAD_MAX + 7) & ~7) + 8;
+};
+// staging offset of a window whose first float sits a (0..7) floats past a 32-byte boundary of the output:
+// off % 4 == a % 4 (shared and global addresses agree modulo 16 bytes), off % 3 == 0 (pixel phase of the background), off >= a
+__device__ __forceinline__ int stage_off(int a) { return (int)((0xF69C3690u >> (4 * a)) & 15u); }
+
+__device__ __forceinline__ void fill_seam_pattern(float* seam, int seam_at, int seamlen, int pitch, int plane, int tid, int nthreads) {
+  for (int j = tid; j < seamlen; j += nthreads) {
+    const int e = j >= seam_at ? j - seam_at : pitch - (seam_at - j);    // element of the plane this float belongs to
+    seam[j] = (e < plane && e % 3 == 1) ? 1.0f : 0.0f;                   // wall [0,1,0]; pad floats are 0
+  }
+}
+
+// Encodes the planes of the first n_emit live snakes of one game to gbase (the game's first row: rows are PITCH apart).
+// keys (optional, when kWantKey): 2 words per row; row_ids (optional): game*8 + snake per row.
+template <class G, bool kWantKey, bool kHint>
+__device__ __forceinline__ void warp_encode_game_v3(const CellView<G>& cv, const Snake& sn, unsigned live_mask, int n_emit,
+                                                    EncodeCtx<G>& ctx, float* gbase, uint64_t* keys, int32_t* row_ids, int gid8) {
+  constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS, N = G::N;
+  using P = PitchGeo<G>;
+  const int lane = lane_id();
+  int prev_end = 0;          // game-relative float offset up to which the output has been handed to the copy engine
+  unsigned rest = live_mask;
+  for (int k = 0; k < n_emit; ++k) {
+    const int vs = __ffs(rest) - 1;
+    rest &= rest - 1;
+    const int vhead = __shfl_sync(kFull, sn.head, vs);
+    const int vlen = __shfl_sync(kFull, sn.len, vs);
+    const int vhp = __shfl_sync(kFull, sn.health, vs);
+    const int vrot = __shfl_sync(kFull, sn.last, vs);
+    const int hy = vhead / SIDE, hx = vhead - hy * SIDE;
+    const float my_hv = (float)(((double)sn.len - ((double)vlen - 0.5)) * 0.04);      // game.py:229,232 in float64
+    const float foodv = (float)((double)(101 - vhp) * 0.01);                            // game.py:244
+    int A, B, Cc, i0;                                                                   // see warp_encode_v2
+    if (vrot == 0)      { A = N;  B = 1;  Cc = (SIDE - 1 - hy) * N + (SIDE - 1 - hx);             i0 = SIDE - 1 - hy; }
+    else if (vrot == 1) { A = 1;  B = -N; Cc = (N - SIDE + hx) * N + (SIDE - 1 - hy);             i0 = hx; }
+    else if (vrot == 2) { A = -N; B = -1; Cc = (N - SIDE + hy) * N + (N - SIDE + hx);             i0 = hy; }
+    else                { A = -1; B = N;  Cc = (SIDE - 1 - hx) * N + (N - SIDE + hy);             i0 = SIDE - 1 - hx; }
+    const int W0 = i0 * 3 * N;
+    const int a = W0 & 7;
+    const int off = stage_off(a);
+    const int base3 = 3 * Cc - W0 + off;
+    float* stage = ctx.cur;
+    if (lane == 0) bulk_wait_read<1>();      // the store that read this buffer two planes ago has finished reading it
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int s = ctx.prev_cur[q];
+      if (s >= 0) { stage[s] = 0.0f; stage[s + 1] = 1.0f; stage[s + 2] = 0.0f; }
+    }
+    __syncwarp();
+    uint64_t k0 = 0, k1 = 0;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane * CPL + q;
+      const int hsq = cv.hs[q];
+      const float hv = __shfl_sync(kFull, my_hv, hsq < 0 ? 0 : hsq);
+      int sidx = -1;
+      if (c < CELLS) {
+        const int y = cv.cy[q], x = cv.cx[q];
+        float t0, t1, t2;
+        if (c == vhead) { t0 = t1 = t2 = -1.0f; }                           // game.py:248
+        else { t0 = (hsq >= 0) ? hv : 0.0f; t1 = cv.f1[q]; t2 = cv.food[q] ? foodv : 0.0f; }
+        sidx = 3 * (A * y + B * x) + base3;
+        stage[sidx] = t0; stage[sidx + 1] = t1; stage[sidx + 2] = t2;
+        if (kWantKey) key_accumulate((uint32_t)(A * y + B * x + Cc), __float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), k0, k1);
+      }
+      ctx.prev_cur[q] = sidx;
+    }
+    if (kWantKey) {
+      k0 = warp_sum_u64(k0); k1 = warp_sum_u64(k1);
+      if (k0 == 0) k0 = 1;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    const int EA = W0 - a, EE = (W0 + P::WIN + 7) & ~7;      // 32-byte aligned cover of the window, plane relative
+    const int plane_off = k * P::PITCH;
+    if (lane == 0) {
+      const int run = plane_off + EA - prev_end;               // wall (and pad) floats between the last window and this one
+      if (run > 0) bulk_s2g<kHint>(gbase + prev_end, ctx.bg + P::SEAM_AT - (plane_off - prev_end), (uint32_t)(run * 4), ctx.policy);
+      bulk_s2g<kHint>(gbase + plane_off + EA, stage + (off - a), (uint32_t)((EE - EA) * 4), ctx.policy);
+      if (k == n_emit - 1 && EE < P::PITCH)                    // the wall after the game's last window
+        bulk_s2g<kHint>(gbase + plane_off + EE, ctx.bg + P::SEAM_AT - (P::PITCH - EE), (uint32_t)((P::PITCH - EE) * 4), ctx.policy);
+      bulk_commit();
+      if (row_ids != nullptr) row_ids[k] = gid8 + vs;
+      if (kWantKey) { keys[2 * k] = k0; keys[2 * k + 1] = k1; }
+    }
+    prev_end = plane_off + EE;
+    ctx.cur = ctx.oth; ctx.oth = stage;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) { const int t = ctx.prev_cur[q]; ctx.prev_cur[q] = ctx.prev_oth[q]; ctx.prev_oth[q] = t; }
+  }
+}
+
 }  // namespace asz

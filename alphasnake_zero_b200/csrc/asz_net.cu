@@ -595,7 +595,7 @@ __global__ void pair_weight_layout_kernel(const __nv_bfloat16* __restrict__ src,
 }
 
 // ---- input preparation: fp32 NHWC planes -> bf16 im2col rows of the first convolution (K = 27 padded to 32) --------
-__global__ void im2col_kernel(const float* __restrict__ planes, int n_img, int real, int pitch, int img_stride, int P_tot,
+__global__ void im2col_kernel(const float* __restrict__ planes, size_t plane_stride, int n_img, int real, int pitch, int img_stride, int P_tot,
                               __nv_bfloat16* __restrict__ out /* [4][P_tot][8] */) {
   const int pos = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (pos >= n_img * img_stride) return;
@@ -605,7 +605,7 @@ __global__ void im2col_kernel(const float* __restrict__ planes, int n_img, int r
 #pragma unroll
   for (int i = 0; i < 32; ++i) k[i] = 0.0f;
   if (y < real && x < real) {
-    const float* pl = planes + (size_t)n * real * real * 3;
+    const float* pl = planes + (size_t)n * plane_stride;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -757,7 +757,8 @@ struct asz_net {
   __nv_bfloat16* w_pair[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
-static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st);
+static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st,
+                            size_t plane_stride = 0);
 
 extern "C" {
 
@@ -885,6 +886,14 @@ int asz_net_forward(asz_net* n, const float* d_planes, int32_t count, float* d_v
   return net_forward_impl(n, d_planes, count, d_values, -1, nullptr, (cudaStream_t)stream);
 }
 
+int asz_net_forward_pitched(asz_net* n, const float* d_planes, int32_t plane_pitch, int32_t count, float* d_values, void* stream) {
+  if (!n || !d_planes || !d_values) { set_error("null argument"); return ASZ_ERR_ARG; }
+  if (plane_pitch < n->real * n->real * 3) { set_error("plane_pitch is smaller than a plane"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(n->device);
+  NvtxRange nvtx("asz:net forward");
+  return net_forward_impl(n, d_planes, count, d_values, -1, nullptr, (cudaStream_t)stream, (size_t)plane_pitch);
+}
+
 int asz_net_debug_layer(asz_net* n, const float* d_planes, int32_t count, int32_t layer, float* d_act, void* stream) {
   if (!n || !d_planes || !d_act) { set_error("null argument"); return ASZ_ERR_ARG; }
   if (count > n->chunk) { set_error("debug export handles one chunk"); return ASZ_ERR_ARG; }
@@ -912,8 +921,9 @@ __global__ void export_act_kernel(const __nv_bfloat16* act, const float* head, i
 }
 }  // namespace asz
 
-static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st) {
-  const size_t plane = (size_t)n->real * n->real * 3;
+static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st,
+                            size_t plane_stride) {
+  const size_t plane = plane_stride ? plane_stride : (size_t)n->real * n->real * 3;     // floats between consecutive input planes
   auto dump = [&](const __nv_bfloat16* act, const float* head, int m) -> int {
     const size_t tot = (size_t)m * n->real * n->real * (head ? 1 : kC);
     export_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(act, head, m, n->real, n->pitch, n->img_stride, n->P_tot, d_act);
@@ -925,7 +935,7 @@ static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, fl
   for (int i0 = 0; i0 < count; i0 += per_pass) {
     const int m = std::min(per_pass, count - i0);
     const int P = m * n->img_stride;
-    im2col_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_planes + (size_t)i0 * plane, m, n->real, n->pitch, n->img_stride, n->P_tot, n->col);
+    im2col_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_planes + (size_t)i0 * plane, plane, m, n->real, n->pitch, n->img_stride, n->P_tot, n->col);
     if (!cuda_ok(cudaGetLastError(), "im2col_kernel")) return ASZ_ERR_CUDA;
     int rc = launch_conv(n, 0, n->col, nullptr, n->act[0], false, m, st);          // alpha_nnet.py:21-22
     if (rc != ASZ_OK) return rc;

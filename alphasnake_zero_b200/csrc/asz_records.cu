@@ -9,6 +9,7 @@
 //   mirror_states = flip(states, axis=2)  (the width axis of [n, h, w, 3])      alpha_snake_zero_trainer.py:93-97
 //   mirror_values = flip(values, axis=1)  (left <-> right)                       alpha_snake_zero_trainer.py:99-100
 // Roofline: HBM bandwidth; algorithmic bytes per sampled record = plane read + 2 plane writes = 3 x 5,292 B at 11x11.
+// Stored planes are asz_plane_pitch() floats apart (written by the pitched fast path of the encode); batches are dense.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -20,7 +21,7 @@ namespace asz {
 struct RecordStore {
   int64_t capacity = 0;      // rows
   int64_t count = 0;         // rows appended so far (host copy; refreshed by the synchronisation in asz_records_append)
-  float* planes = nullptr;   // [capacity][plane]
+  float* planes = nullptr;   // [capacity][pitch]: rows start on 32-byte sectors (asz_plane_pitch)
   float* values = nullptr;   // [capacity][3]
   int32_t* ids = nullptr;    // [capacity] game*8 + snake of every record
   int32_t* turns = nullptr;  // [capacity] append call (root turn) that produced the record
@@ -42,7 +43,7 @@ __global__ void records_values_kernel(const float* __restrict__ root_q, const in
 // One CTA per sampled record: X[i] = planes[idx[i]], V[i] = values[idx[i]]; when mirror: X[n + i] = flip(X[i], width axis),
 // V[n + i] = reversed V[i].  A plane row is N pixels x 3 floats; the flipped row is the same pixels in reverse order.
 __global__ void __launch_bounds__(256) records_gather_kernel(const float* __restrict__ planes, const float* __restrict__ values,
-                                                             const int64_t* __restrict__ idx, int n, int N, int mirror,
+                                                             const int64_t* __restrict__ idx, int n, int N, int pitch, int mirror,
                                                              int64_t count, float* __restrict__ X, float* __restrict__ V) {
   const int i = (int)blockIdx.x;
   if (i >= n) return;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) records_gather_kernel(const float* __rest
     for (int e = (int)threadIdx.x; e < plane; e += (int)blockDim.x) { x0[e] = __int_as_float(0x7fc00000); if (mirror) x1[e] = __int_as_float(0x7fc00000); }
     return;
   }
-  const float* src = planes + (size_t)r * plane;
+  const float* src = planes + (size_t)r * pitch;
   for (int e = (int)threadIdx.x; e < plane; e += (int)blockDim.x) {
     const float v = src[e];
     x0[e] = v;
@@ -80,12 +81,12 @@ static int records_reserve(asz_engine* e, int64_t need_rows, cudaStream_t st) {
   if (cap > 0x7fffffff) cap = 0x7fffffff;
   if (cap < need_rows) { set_error("record store cannot grow past 2^31 - 1 rows"); return ASZ_ERR_CAPACITY; }
   float *pl = nullptr, *va = nullptr; int32_t *ids = nullptr, *tu = nullptr;
-  ASZ_CUDA(cudaMalloc(&pl, (size_t)cap * e->plane * sizeof(float) + 32));
+  ASZ_CUDA(cudaMalloc(&pl, (size_t)cap * e->pitch * sizeof(float) + 32));
   ASZ_CUDA(cudaMalloc(&va, (size_t)cap * 3 * sizeof(float)));
   ASZ_CUDA(cudaMalloc(&ids, (size_t)cap * sizeof(int32_t)));
   ASZ_CUDA(cudaMalloc(&tu, (size_t)cap * sizeof(int32_t)));
   const size_t n = (size_t)r->count;
-  ASZ_CUDA(cudaMemcpyAsync(pl, r->planes, n * e->plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ASZ_CUDA(cudaMemcpyAsync(pl, r->planes, n * e->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ASZ_CUDA(cudaMemcpyAsync(va, r->values, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ASZ_CUDA(cudaMemcpyAsync(ids, r->ids, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   ASZ_CUDA(cudaMemcpyAsync(tu, r->turns, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -117,7 +118,7 @@ int asz_records_enable(asz_engine* e, int64_t capacity_rows) {
   RecordStore* r = new RecordStore();
   e->records = r;
   r->capacity = capacity_rows;
-  ASZ_CUDA(cudaMalloc(&r->planes, (size_t)capacity_rows * e->plane * sizeof(float) + 32));
+  ASZ_CUDA(cudaMalloc(&r->planes, (size_t)capacity_rows * e->pitch * sizeof(float) + 32));
   ASZ_CUDA(cudaMalloc(&r->values, (size_t)capacity_rows * 3 * sizeof(float)));
   ASZ_CUDA(cudaMalloc(&r->ids, (size_t)capacity_rows * sizeof(int32_t)));
   ASZ_CUDA(cudaMalloc(&r->turns, (size_t)capacity_rows * sizeof(int32_t)));
@@ -141,6 +142,7 @@ int asz_records_append(asz_engine* e, const float* d_root_q, int64_t* h_count, v
   memset(&a, 0, sizeof a);
   a.flags = ASZ_STEP_ENCODE; a.spawn_mode = ASZ_SPAWN_NONE;
   a.d_planes = r->planes; a.d_row_ids = r->ids; a.max_rows = (int32_t)r->capacity; a.row_base = (int32_t)r->count;
+  a.plane_pitch = e->pitch;
   a.d_row_count = e->row_count;
   rc = asz_env_step(e, &a, stream);
   if (rc != ASZ_OK) return rc;
@@ -193,7 +195,7 @@ int asz_records_gather(asz_engine* e, const int64_t* d_idx, int32_t n, int32_t m
   DeviceGuard guard(e->device);
   NvtxRange nvtx("asz:records gather + mirror");
   RecordStore* r = e->records;
-  records_gather_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(r->planes, r->values, d_idx, n, 2 * e->cfg.side - 1, mirror ? 1 : 0, r->count,
+  records_gather_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(r->planes, r->values, d_idx, n, 2 * e->cfg.side - 1, e->pitch, mirror ? 1 : 0, r->count,
                                                             d_X, d_V);
   return cuda_ok(cudaGetLastError(), "records_gather_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
 }

@@ -41,6 +41,7 @@ class Engine:
             check(self.L.asz_engine_create(C.byref(h), C.byref(cfg)))
         self.h = h
         dev = self.device
+        self.pitch = int(self.L.asz_plane_pitch(self.h))      # floats between rows of the engine's plane buffers (32-byte rows)
         self.max_rows = games * snakes
         self._planes = None
         self.row_ids = torch.zeros(self.max_rows, dtype=torch.int32, device=dev)
@@ -66,10 +67,23 @@ class Engine:
 
     @property
     def planes(self):
-        """[G*S, N, N, 3] float32 batch buffer (allocated on first use)."""
+        """[G*S, N, N, 3] float32 batch buffer (allocated on first use).  Rows are `pitch` floats apart (the plane size rounded
+        up to 8 floats: every plane starts on a 32-byte sector, the fast path of the encode kernel), so this is a strided
+        view; `.contiguous()` / indexing give dense copies."""
         if self._planes is None:
-            self._planes = torch.empty(self.max_rows, self.N, self.N, 3, dtype=torch.float32, device=self.device)
+            self._planes_flat = torch.zeros(self.max_rows * self.pitch + 8, dtype=torch.float32, device=self.device)
+            self._planes = torch.as_strided(self._planes_flat, (self.max_rows, self.N, self.N, 3), (self.pitch, 3 * self.N, 3, 1))
         return self._planes
+
+    def _plane_pitch_of(self, t):
+        """0 for a dense [rows, N, N, 3] tensor, self.pitch for a view with the engine's row pitch"""
+        if tuple(t.shape[1:]) != (self.N, self.N, 3) or t.dtype != torch.float32:
+            raise AszError("planes must be float32 [rows, %d, %d, 3]" % (self.N, self.N))
+        if t.shape[0] <= 1 or t.is_contiguous():
+            return 0 if t.is_contiguous() else self.pitch
+        if tuple(t.stride()) == (self.pitch, 3 * self.N, 3, 1):
+            return self.pitch
+        raise AszError("planes must be contiguous or have the engine's row pitch")
 
     def reset(self):
         check(self.L.asz_reset(self.h, self.stream))
@@ -108,6 +122,7 @@ class Engine:
             pl = self.planes if planes is None else planes
             a.d_planes = pl.data_ptr()
             a.max_rows = pl.shape[0]
+            a.plane_pitch = self._plane_pitch_of(pl)
         a.d_row_ids = self.row_ids.data_ptr()
         if keys:
             if self.keys is None:
@@ -242,7 +257,8 @@ class Engine:
     def records_views(self):
         """(planes [n, N, N, 3], values [n, 3], ids [n] int32 = game*8 + snake, turns [n] int32) views of the store"""
         n = max(self.records_count(), 1)       # the store may have grown: wrap what is filled, not a remembered capacity
-        pl = self._wrap(self.L.asz_records_planes(self.h), (n, self.N, self.N, 3), torch.float32)
+        flat = self._wrap(self.L.asz_records_planes(self.h), (n * self.pitch,), torch.float32)      # rows are `pitch` floats apart
+        pl = torch.as_strided(flat, (n, self.N, self.N, 3), (self.pitch, 3 * self.N, 3, 1))
         va = self._wrap(self.L.asz_records_values(self.h), (n, 3), torch.float32)
         ids = self._wrap(self.L.asz_records_ids(self.h), (n,), torch.int32)
         tu = self._wrap(self.L.asz_records_turns(self.h), (n,), torch.int32)

@@ -100,13 +100,20 @@ class NativeNet:
     def forward(self, planes, out=None):
         """planes [n, N, N, 3] float32 cuda (contiguous) -> [n, 3] float32 raw outputs."""
         assert planes.is_cuda and planes.dtype == torch.float32
-        planes = planes.contiguous()
         n = planes.shape[0]
+        pitch = 0
+        if n > 1 and not planes.is_contiguous() and tuple(planes.stride()[1:]) == (3 * self.N, 3, 1) and planes.stride(0) >= 3 * self.N * self.N:
+            pitch = planes.stride(0)            # rows of an engine plane buffer (32-byte aligned rows): read in place
+        else:
+            planes = planes.contiguous()
         if out is None:
             out = torch.empty(n, 3, dtype=torch.float32, device=planes.device)
         if n > 0:
             st = C.c_void_p(torch.cuda.current_stream(planes.device).cuda_stream)
-            check(self.L.asz_net_forward(self.h, C.c_void_p(planes.data_ptr()), n, C.c_void_p(out.data_ptr()), st))
+            if pitch:
+                check(self.L.asz_net_forward_pitched(self.h, C.c_void_p(planes.data_ptr()), pitch, n, C.c_void_p(out.data_ptr()), st))
+            else:
+                check(self.L.asz_net_forward(self.h, C.c_void_p(planes.data_ptr()), n, C.c_void_p(out.data_ptr()), st))
         return out
 
     def debug_layer(self, planes, layer):

@@ -97,7 +97,8 @@ typedef struct {
   int32_t spawn_mode;
   const uint8_t* d_actions;      /* [G*8] relative move per (game, snake id); read where the snake is alive */
   const int32_t* d_spawn_cells;  /* [G] for ASZ_SPAWN_REPLAY */
-  float* d_planes;               /* [max_rows][2*side-1][2*side-1][3] float32 NHWC, rows compacted; 32-byte aligned */
+  float* d_planes;               /* [max_rows][2*side-1][2*side-1][3] float32 NHWC, rows compacted; 32-byte aligned; rows are
+                                    plane_pitch floats apart */
   int32_t* d_row_ids;            /* [max_rows] game*8 + snake of every row written */
   uint64_t* d_keys;              /* [max_rows*2] when ASZ_STEP_KEYS */
   int32_t max_rows;
@@ -106,6 +107,10 @@ typedef struct {
   int8_t* d_rewards;             /* [G*8] final rewards of games that ended in this tic: 0 none, 1, -1 (may be NULL) */
   int32_t row_base;              /* rows are written at [row_base, row_base + n) of d_planes / d_row_ids / d_keys; max_rows
                                     stays the absolute capacity (rows past it are dropped, *d_row_count still counts them) */
+  int32_t plane_pitch;           /* floats between consecutive rows of d_planes: 0 (or asz_plane_floats) = dense rows;
+                                    asz_plane_pitch() = the plane size rounded up to 8 floats, so that every row starts on a
+                                    32-byte sector: the layout of the engine's own buffers and the fast path of the encode
+                                    (the pad floats after each plane are written but carry no meaning) */
 } asz_step_args;
 
 /* Enqueues one fused launch.  Row order inside d_planes is unspecified across games (rows of one game are
@@ -135,10 +140,12 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals);
  * staging-buffer wait (inside encode), unused; all zero in the product build.  Synchronous. */
 int asz_internal_profile(asz_engine* e, uint64_t* h_cycles);
 int asz_internal_state(asz_engine* e, void** d_ptrs);
-/* device pointer of the engine's internal plane buffer (capacity G*S rows) and row-id buffer */
+/* device pointer of the engine's internal plane buffer (capacity G*S rows, asz_plane_pitch() floats apart) and row-id buffer */
 float* asz_internal_planes(asz_engine* e);
 int32_t* asz_internal_row_ids(asz_engine* e);
 size_t asz_plane_floats(const asz_engine* e);
+/* row pitch (floats) of the engine's internal plane buffers: asz_plane_floats rounded up to a multiple of 8 */
+size_t asz_plane_pitch(const asz_engine* e);
 
 /* ---- search: Agent.make_moves (agent.py:25-111) = epochs x (MCTSMPGameRunner.run, mp_game_runner.py:85-115, over
  * MCTSAgent.make_moves, agent.py:161-223) ------------------------------------------------------------------------
@@ -220,7 +227,7 @@ int asz_records_clear(asz_engine* e);
  * (states flipped along the width axis, values reversed: :93-100) follow the n originals.  d_idx [n] int64 DEVICE
  * indices (the reference draws them with random.sample on the host); d_X [(mirror ? 2 : 1) * n][plane], d_V [..][3]. */
 int asz_records_gather(asz_engine* e, const int64_t* d_idx, int32_t n, int32_t mirror, float* d_X, float* d_V, void* stream);
-float* asz_records_planes(asz_engine* e);     /* device [capacity][plane] */
+float* asz_records_planes(asz_engine* e);     /* device [capacity][asz_plane_pitch()] */
 float* asz_records_values(asz_engine* e);     /* device [capacity][3] */
 int32_t* asz_records_ids(asz_engine* e);      /* device [capacity] game*8 + snake */
 int32_t* asz_records_turns(asz_engine* e);    /* device [capacity] index of the append call */
@@ -261,6 +268,8 @@ int asz_net_set_variant(asz_net* net, int32_t variant);
 /* d_planes [count][2*side-1][2*side-1][3] float32 NHWC -> d_values [count][3] float32 tanh outputs (no obstacle mask;
  * asz_obstacle_mask applies AlphaNNet.v's mask).  bf16 operands, fp32 accumulation. */
 int asz_net_forward(asz_net* net, const float* d_planes, int32_t count, float* d_values, void* stream);
+/* the same for rows that are plane_pitch floats apart (asz_plane_pitch(): the engine's own plane buffers) */
+int asz_net_forward_pitched(asz_net* net, const float* d_planes, int32_t plane_pitch, int32_t count, float* d_values, void* stream);
 /* test hook: runs the tower up to convolution `layer` (0 = first conv, 1..8 = residual convs in order) and exports
  * that layer's output as float32 [count][2*side-1][2*side-1][128] ([..][1] for layer 8: the fused 1x1 head conv) */
 int asz_net_debug_layer(asz_net* net, const float* d_planes, int32_t count, int32_t layer, float* d_act, void* stream);

@@ -11,14 +11,14 @@ if len(sys.argv) > 2 and sys.argv[1] == "build-variant":       # python tools/en
     out = os.path.join(ROOT, "tools", "libasz_b200_%s.so" % sys.argv[2])
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                            "--expt-relaxed-constexpr"] + sys.argv[3:] + ["-shared", "-o", out] +
-                          [os.path.join(csrc, f) for f in ("asz_env.cu", "asz_mcts.cu", "asz_net.cu")] + ["-lcuda"])
+                          [os.path.join(csrc, f) for f in ("asz_env.cu", "asz_mcts.cu", "asz_net.cu", "asz_records.cu")] + ["-lcuda", "-ldl"])
     print(out)
     sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     csrc = os.path.join(ROOT, "alphasnake_zero_b200", "csrc")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
            "--expt-relaxed-constexpr", "-DASZ_ENV_PROFILE", "-shared", "-o", PROF_LIB] + \
-          [os.path.join(csrc, f) for f in ("asz_env.cu", "asz_mcts.cu", "asz_net.cu")] + ["-lcuda"]
+          [os.path.join(csrc, f) for f in ("asz_env.cu", "asz_mcts.cu", "asz_net.cu", "asz_records.cu")] + ["-lcuda", "-ldl"]
     subprocess.check_call(cmd)
     print(PROF_LIB)
     sys.exit(0)
