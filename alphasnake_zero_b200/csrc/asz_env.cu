@@ -94,6 +94,7 @@ struct EnvSmem {
   using G = Geo<SIDE>;
   static constexpr int BG = PITCHED ? PitchGeo<G>::SEAMLEN : EncGeo<G>::BGLEN;          // per-CTA constant wall buffer (floats)
   static constexpr int WSTAGE = PITCHED ? PitchGeo<G>::WSTAGE : EncGeo<G>::WSTAGE;      // floats per staging buffer
+  static constexpr int LUT_BYTES = PITCHED ? PitchLut<G>::BYTES : 0;                    // index / value tables of warp_encode_game_v3b
 };
 
 template <int SIDE, int WARPS, int MINB, bool HINTS, bool ACTS, bool PITCHED>
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   uint16_t* sb = reinterpret_cast<uint16_t*>(s_bg + SM::BG + WARPS * 2 * SM::WSTAGE) + warp * G::PC;
   float* s_lut = reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(s_bg + SM::BG + WARPS * 2 * SM::WSTAGE) + WARPS * G::PC);
   for (int d = (int)threadIdx.x; d < G::PC + 8; d += WARPS * 32) s_lut[d] = (float)((double)d * 0.02);   // game.py:239, float64 product
+  unsigned char* s_plut = reinterpret_cast<unsigned char*>(s_lut + G::PC + 8);
+  if constexpr (PITCHED) fill_pitch_luts<G>(s_plut, (int)threadIdx.x, WARPS * 32);
   const bool enc = (p.flags & ASZ_STEP_ENCODE) != 0;
   if (enc) {
     if constexpr (PITCHED) fill_seam_pattern(s_bg, PitchGeo<G>::SEAM_AT, PitchGeo<G>::SEAMLEN, PitchGeo<G>::PITCH, G::PLANE, (int)threadIdx.x, WARPS * 32);
@@ -117,6 +120,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   }
   __syncthreads();
   EncodeCtx<G> ctx;
+  EncodeCtxP<G> ctxp;
+  ctxp.cur = stage0; ctxp.oth = stage0 + SM::WSTAGE; ctxp.seam = s_bg; ctxp.policy = HINTS ? l2_policy_evict_first() : 0ull;
+  ctxp.lin = reinterpret_cast<const int16_t*>(s_plut);
+  ctxp.hv = reinterpret_cast<const float*>(s_plut + PitchLut<G>::LIN * 2);
+  ctxp.food = ctxp.hv + PitchLut<G>::HV;
+  ctxp.cur_rot = ctxp.oth_rot = -1; ctxp.cur_base = ctxp.oth_base = 0;
   ctx.cur = stage0; ctx.oth = stage0 + SM::WSTAGE; ctx.bg = s_bg; ctx.policy = HINTS ? l2_policy_evict_first() : 0ull;
 #pragma unroll
   for (int q = 0; q < G::CPL; ++q) { ctx.prev_cur[q] = -1; ctx.prev_oth[q] = -1; }
@@ -275,8 +284,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
           const int n_emit = min(n_rows, p.max_rows - row);
           if (n_emit > 0) {
             float* gbase = p.planes + (size_t)row * PitchGeo<G>::PITCH;
+#ifdef ASZ_ENC_V3A       // A/B: the first pitched encode (per-lane restore bookkeeping, select chains, float64 products per plane)
             if (p.flags & ASZ_STEP_KEYS) warp_encode_game_v3<G, true, HINTS>(cv, sn, live_mask, n_emit, ctx, gbase, p.keys + 2 * (size_t)row, p.row_ids + row, g * 8);
             else warp_encode_game_v3<G, false, HINTS>(cv, sn, live_mask, n_emit, ctx, gbase, nullptr, p.row_ids + row, g * 8);
+#else
+            if (p.flags & ASZ_STEP_KEYS) warp_encode_game_v3b<G, true, HINTS>(cv, sn, live_mask, n_emit, ctxp, gbase, p.keys + 2 * (size_t)row, p.row_ids + row, g * 8);
+            else warp_encode_game_v3b<G, false, HINTS>(cv, sn, live_mask, n_emit, ctxp, gbase, nullptr, p.row_ids + row, g * 8);
+#endif
           }
         }
         while (rest) {
@@ -343,7 +357,7 @@ struct EnvLaunch {
   static size_t smem_bytes() {
     using SM = EnvSmem<SIDE, PITCHED>;
     return (size_t)(SM::BG + WARPS * 2 * SM::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t) +
-           (size_t)(G::PC + 8) * sizeof(float);
+           (size_t)(G::PC + 8) * sizeof(float) + (size_t)SM::LUT_BYTES;
   }
   template <int MINB, bool HINTS, bool ACTS, bool PITCHED>
   static int launch(const EnvParams& p, cudaStream_t st) {
@@ -358,6 +372,15 @@ struct EnvLaunch {
                                         cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
         return ASZ_ERR_CUDA;
       if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
+      if (getenv("ASZ_DEBUG_OCC")) {   // experiments: CTAs the runtime expects to keep resident per SM with this shared-memory size
+        int nb = -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS, PITCHED>, WARPS * 32, smem_bytes<PITCHED>());
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS, PITCHED>);
+        fprintf(stderr, "[asz] env_step_kernel<%d,%d,%d,%d,%d,%d>: %d CTAs/SM expected, %zu B dynamic + %zu B static smem, %d regs, carveout pref %d\n",
+                SIDE, WARPS, MINB, (int)HINTS, (int)ACTS, (int)PITCHED, nb, smem_bytes<PITCHED>(), fa.sharedSizeBytes, fa.numRegs,
+                fa.preferredShmemCarveout);
+      }
     }
     const int blocks = std::min((p.G + WARPS - 1) / WARPS, p.n_sm * MINB);
     env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS, PITCHED><<<blocks, WARPS * 32, smem_bytes<PITCHED>(), st>>>(p);

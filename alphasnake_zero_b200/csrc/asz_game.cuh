@@ -615,4 +615,153 @@ __device__ __forceinline__ void warp_encode_game_v3(const CellView<G>& cv, const
   }
 }
 
+// ---- v3b: the same emission with table-driven indices and no per-lane bookkeeping ------------------------------------
+// What v3 still spends per plane: the rotation / recentring select chains, two float64 products, the "which stage index did
+// each of my cells go to" arrays of both staging buffers (8 registers, swapped every plane, spilled) and the per-cell
+// own-head selects.  v3b keeps per staging buffer only the (rotation, base) pair of the plane it holds -- warp-uniform --
+// and reads the rotation-dependent linear term of a cell, 3 * (A*y + B*x), from a 1 KB table in shared memory, so the
+// restore pass recomputes its indices instead of remembering them; head and food values come from tables (same float64
+// products, evaluated once per CTA); the viewer's own head is patched by the one lane that owns the cell.
+template <class G>
+struct PitchLut {
+  static constexpr int LIN = 4 * G::PC;                 // int16 [4 rotations][PC cells]: 3 * (A*y + B*x)
+  static constexpr int HV = 2 * G::CELLS + 2;           // float [len_s - len_viewer + CELLS]: ((d + 0.5) * 0.04), game.py:229,232
+  static constexpr int FOOD = 128;                      // float [101 - health] for 0 <= 101 - health < 128, game.py:244
+  static constexpr int BYTES = ((LIN * 2 + (HV + FOOD) * 4 + 15) / 16) * 16;
+};
+template <class G>
+struct EncodeCtxP {
+  float* cur; float* oth;        // staging buffers (see EncodeCtx)
+  const float* seam;
+  uint64_t policy;
+  const int16_t* lin; const float* hv; const float* food;
+  int cur_rot, cur_base, oth_rot, oth_base;     // plane each buffer still holds (rot < 0: background only)
+};
+template <class G>
+__device__ __forceinline__ void fill_pitch_luts(unsigned char* raw, int tid, int nthreads) {
+  using L = PitchLut<G>;
+  int16_t* lin = reinterpret_cast<int16_t*>(raw);
+  float* hv = reinterpret_cast<float*>(raw + L::LIN * 2);
+  float* food = hv + L::HV;
+  constexpr int SIDE = G::SIDE, N = G::N;
+  for (int i = tid; i < L::LIN; i += nthreads) {
+    const int rot = i / G::PC, c = i - rot * G::PC;
+    const int cc = c < G::CELLS ? c : 0;                 // padding cells alias cell 0 (only ever used by the restore pass)
+    const int y = cc / SIDE, x = cc - y * SIDE;
+    const int v = rot == 0 ? N * y + x : rot == 1 ? y - N * x : rot == 2 ? -(N * y + x) : -(y - N * x);
+    lin[i] = (int16_t)(3 * v);
+  }
+  for (int i = tid; i < L::HV; i += nthreads) hv[i] = (float)(((double)(i - G::CELLS) + 0.5) * 0.04);
+  for (int i = tid; i < L::FOOD; i += nthreads) food[i] = (float)((double)i * 0.01);
+}
+template <class G>
+__device__ __forceinline__ void load_lin(const int16_t* lin, int rot, int lane, int (&out)[G::CPL]) {
+  const int16_t* p = lin + rot * G::PC + lane * G::CPL;
+  if constexpr (G::CPL % 4 == 0) {
+#pragma unroll
+    for (int q4 = 0; q4 < G::CPL / 4; ++q4) {
+      const uint2 v = reinterpret_cast<const uint2*>(p)[q4];
+      out[4 * q4] = (int)(int16_t)(v.x & 0xFFFFu); out[4 * q4 + 1] = (int)v.x >> 16;
+      out[4 * q4 + 2] = (int)(int16_t)(v.y & 0xFFFFu); out[4 * q4 + 3] = (int)v.y >> 16;
+    }
+  } else {
+#pragma unroll
+    for (int q2 = 0; q2 < G::CPL / 2; ++q2) {
+      const uint32_t v = reinterpret_cast<const uint32_t*>(p)[q2];
+      out[2 * q2] = (int)(int16_t)(v & 0xFFFFu); out[2 * q2 + 1] = (int)v >> 16;
+    }
+  }
+}
+
+template <class G, bool kWantKey, bool kHint>
+__device__ __forceinline__ void warp_encode_game_v3b(const CellView<G>& cv, const Snake& sn, unsigned live_mask, int n_emit,
+                                                     EncodeCtxP<G>& ctx, float* gbase, uint64_t* keys, int32_t* row_ids, int gid8) {
+  constexpr int SIDE = G::SIDE, CPL = G::CPL, CELLS = G::CELLS, N = G::N, U = G::SIDE - 1;
+  using P = PitchGeo<G>;
+  const int lane = lane_id();
+  int prev_end = 0;
+  unsigned rest = live_mask;
+  for (int k = 0; k < n_emit; ++k) {
+    const int vs = __ffs(rest) - 1;
+    rest &= rest - 1;
+    const int vhead = __shfl_sync(kFull, sn.head, vs);
+    const int vlen = __shfl_sync(kFull, sn.len, vs);
+    const int vhp = __shfl_sync(kFull, sn.health, vs);
+    const int vrot = __shfl_sync(kFull, sn.last, vs);
+    const int hy = vhead / SIDE, hx = vhead - hy * SIDE;
+    const float my_hv = ctx.hv[sn.len - vlen + CELLS];                                 // game.py:229,232
+    const int fi = 101 - vhp;
+    const float foodv = (unsigned)fi < (unsigned)PitchLut<G>::FOOD ? ctx.food[fi] : (float)((double)fi * 0.01);   // game.py:244
+    // recentring + rot90 (game.py:249-257), see warp_encode_v2: pixel of cell (y, x) = A*y + B*x + Cc, window row i0;
+    // D = 3*Cc - W0 in closed form per rotation
+    const int t = (vrot & 1) ? hy : hx;                      // rot0: hx, rot1: hy, rot2: hx, rot3: hy
+    const int r = (vrot & 1) ? hx : hy;                      // rot0: hy, rot1: hx, rot2: hy, rot3: hx
+    const bool flip_t = (vrot == 0) || (vrot == 1);          // D uses (U - t) for rot 0, 1 and (U + t) for rot 2, 3
+    const bool far = (vrot == 1) || (vrot == 2);             // ... plus U*N for rot 1, 2
+    const int D = 3 * ((flip_t ? U - t : U + t) + (far ? U * N : 0));
+    const int i0 = (vrot == 0 || vrot == 3) ? U - r : r;     // rot0: U-hy, rot1: hx, rot2: hy, rot3: U-hx
+    const int W0 = i0 * 3 * N;
+    const int a = W0 & 7;
+    const int off = stage_off(a);
+    const int base3 = D + off;
+    float* stage = ctx.cur;
+    if (lane == 0) bulk_wait_read<1>();      // the store that read this buffer two planes ago has finished reading it
+    __syncwarp();
+    if (ctx.cur_rot >= 0) {                  // warp-uniform: put the background back where that plane's cells were scattered
+      int lin[CPL];
+      load_lin<G>(ctx.lin, ctx.cur_rot, lane, lin);
+      const int b = ctx.cur_base;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) { float* d = stage + (b + lin[q]); d[0] = 0.0f; d[1] = 1.0f; d[2] = 0.0f; }
+      __syncwarp();
+    }
+    int lin[CPL];
+    load_lin<G>(ctx.lin, vrot, lane, lin);
+    uint64_t k0 = 0, k1 = 0;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane * CPL + q;
+      const int hsq = cv.hs[q];
+      const float hv = __shfl_sync(kFull, my_hv, hsq < 0 ? 0 : hsq);
+      if (c < CELLS) {
+        float t0 = (hsq >= 0) ? hv : 0.0f, t1 = cv.f1[q], t2 = cv.food[q] ? foodv : 0.0f;
+        if (kWantKey) {
+          if (c == vhead) { t0 = t1 = t2 = -1.0f; }
+          const int Cc = (D + W0) / 3;
+          key_accumulate((uint32_t)(lin[q] / 3 + Cc), __float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), k0, k1);
+        }
+        float* d = stage + (base3 + lin[q]);
+        d[0] = t0; d[1] = t1; d[2] = t2;
+      }
+    }
+    if (lane == vhead / CPL) {               // game.py:248: the viewer's own head is -1 in all channels (same lane wrote the cell above)
+      float* d = stage + (base3 + (int)ctx.lin[vrot * G::PC + vhead]);
+      d[0] = -1.0f; d[1] = -1.0f; d[2] = -1.0f;
+    }
+    if (kWantKey) {
+      k0 = warp_sum_u64(k0); k1 = warp_sum_u64(k1);
+      if (k0 == 0) k0 = 1;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    const int EA = W0 - a, EE = (W0 + P::WIN + 7) & ~7;
+    const int plane_off = k * P::PITCH;
+    if (lane == 0) {
+      const int run = plane_off + EA - prev_end;
+      if (run > 0) bulk_s2g<kHint>(gbase + prev_end, ctx.seam + P::SEAM_AT - (plane_off - prev_end), (uint32_t)(run * 4), ctx.policy);
+      bulk_s2g<kHint>(gbase + plane_off + EA, stage + (off - a), (uint32_t)((EE - EA) * 4), ctx.policy);
+      if (k == n_emit - 1 && EE < P::PITCH)
+        bulk_s2g<kHint>(gbase + plane_off + EE, ctx.seam + P::SEAM_AT - (P::PITCH - EE), (uint32_t)((P::PITCH - EE) * 4), ctx.policy);
+      bulk_commit();
+      if (row_ids != nullptr) row_ids[k] = gid8 + vs;
+      if (kWantKey) { keys[2 * k] = k0; keys[2 * k + 1] = k1; }
+    }
+    prev_end = plane_off + EE;
+    ctx.cur = ctx.oth; ctx.oth = stage;
+    const int orot = ctx.oth_rot, obase = ctx.oth_base;
+    ctx.oth_rot = vrot; ctx.oth_base = base3;
+    ctx.cur_rot = orot; ctx.cur_base = obase;
+  }
+}
+
 }  // namespace asz

@@ -118,7 +118,23 @@ def test_native_search_with_compaction_inside_a_turn():
     assert n >= 2
 
 
-def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, table_log2, sync_steps=False, want_mid=False):
+# BASELINE.json's own search shapes -- breadth 100 / depth 8 (configs[2]), breadth 200 (configs[3]) and 19x19 with
+# 8 snakes at breadth 400 (configs[4]) from a mid-game start (3-5 live snakes: depth 2-6 instead of one tic per sub-game, deaths,
+# evictions, table compactions) -- at the game counts the single-threaded CPU oracle replays in about half a minute each
+# (768 of 4,096 games = 73,728 sub-games and about 1.2 million node visits per root turn; the per-game work is independent
+# of the game count, and the full 4,096-game run is checked for overflow / collisions by bench.py's self-play leg).
+@pytest.mark.parametrize("side,S,G,D,breadth,turns,table_log2,warm,compactions", [
+    (11, 4, 768, 8, 100, 2, 0, 6, 0),
+    (11, 4, 384, 8, 200, 2, 0, 12, 0),
+    (19, 8, 16, 8, 400, 12, 20, 40, 1)])
+def test_native_search_at_baseline_config_shapes(side, S, G, D, breadth, turns, table_log2, warm, compactions):
+    n = _native_search_against_oracle(side, S, G, D, breadth, 2.0, True, turns, table_log2, warm_tics=warm, dump_every=97)
+    assert n >= compactions, "expected at least %d table compactions, saw %d" % (compactions, n)
+
+
+def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, table_log2, sync_steps=False, want_mid=False,
+                                  warm_tics=0, dump_every=5):
+    import os
     import torch
     from oracle import oracle as orc
     seed = 77
@@ -129,6 +145,15 @@ def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns,
     games = []
     for gi in range(G):
         g = orc.OracleGame(side, side, S, 1); g.init_native(seed, gi, 0); g.set_ids(gi, 0); games.append(g)
+    if warm_tics:
+        # games of every age before the search starts: uniform-random play with in-place reset, the same Philox streams on both sides
+        for _ in range(warm_tics):
+            eng.step(spawn_mode=2, tic=True, encode=False, auto_reset=True, random_actions=True)
+        orc.env_run(G, side, side, S, 1, 0.15, seed, warm_tics, encode=False, n_threads=os.cpu_count() or 1, games=games)
+        for g_i in range(0, G, dump_every):
+            assert_dump_equal(eng.get_state(g_i), games[g_i].dump(), "game %d after the warm-up" % g_i)
+        live_counts = [g.n_live for g in games]
+        assert min(live_counts) >= 2 and len(set(live_counts)) > 1        # running games with different numbers of snakes
     agent = orc.OracleAgent(base=base, training=training, max_depth=D, max_breadth=breadth)
     done = [False] * G
     compactions, last_occupied, last_inserts = 0, 0, 0
@@ -174,7 +199,7 @@ def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns,
             if games[g_i].tic(root_moves[r0:r0 + n].astype(np.int32), spawn_mode=2, chance=0.15, seed=seed):
                 done[g_i] = True
             r0 += n
-        for g_i in range(0, G, 5):
+        for g_i in range(0, G, dump_every):
             assert_dump_equal(eng.get_state(g_i), games[g_i].dump(), "root game %d after turn %d" % (g_i, t))
     st = eng.search_stats()
     assert st["compactions"] >= compactions, (st, compactions)
