@@ -162,9 +162,92 @@ def cpu_baseline(target_s=12.0):
                       % (g, tics, st["planes"] / st["steps"], cores, dt)}
 
 
+REF_CODE = os.path.join(ROOT, "baseline", "_ref", "code")
+
+
+def _import_reference():
+    """the UNMODIFIED reference (baseline/_ref/code, vendored by baseline/vendor_reference.py from /root/reference) with the one
+    NumPy >= 2.3 shim of SURVEY.md 8(c): Game.make_state returns an ndarray subclass that still has .tostring (agent.py:175)"""
+    import numpy as np
+    if not os.path.isdir(os.path.join(REF_CODE, "utils")):
+        return None
+    if REF_CODE not in sys.path:
+        sys.path.insert(0, REF_CODE)
+    import utils.agent as ra
+    import utils.game as rg
+    import utils.mp_game_runner as rr
+    if not getattr(rg.Game, "_asz_shim", False):
+        class _Sub(np.ndarray):
+            def tostring(self):
+                return self.tobytes()
+        orig = rg.Game.make_state
+        rg.Game.make_state = lambda self, you, last_move: orig(self, you, last_move).view(_Sub)
+        rg.Game._asz_shim = True
+    return rg, ra, rr
+
+
+def python_reference_env(target_s=6.0):
+    """the reference's own Game (pure Python) with uniform-random moves, tic + get_states() every tic, one core."""
+    import random
+    mods = _import_reference()
+    if mods is None:
+        return {"unavailable": "baseline/_ref/code is missing (run baseline/vendor_reference.py where /root/reference exists)"}
+    rg = mods[0]
+    random.seed(0)
+    g = rg.Game(0, SIDE, SIDE, SNAKES, HEALTH_DEC)
+    steps = planes = 0
+    t0 = time.time()
+    while time.time() - t0 < target_s:
+        for _ in range(50):
+            if g.tic([random.randrange(3) for _ in g.snakes]) != 0:
+                g = rg.Game(0, SIDE, SIDE, SNAKES, HEALTH_DEC)
+            else:
+                planes += len(g.get_states())
+            steps += 1
+    dt = time.time() - t0
+    return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "unmodified reference utils/game.py: Game.tic + Game.get_states() with uniform-random moves, %d tics, %.2f planes/step, "
+                      "single core (the reference is single threaded), %.1f s" % (steps, planes / max(steps, 1), dt)}
+
+
+def python_reference_selfplay(games=4, breadth=50, depth=8):
+    """BASELINE.md 3.2 / configs[0], bounded: the unmodified reference Agent.make_moves (MCTSAgent + MCTSMPGameRunner inside) for one
+    root turn, with a torch-CPU fp32 network of identical architecture behind the AlphaNNet.v contract (TensorFlow is not
+    installable here)."""
+    import contextlib
+    import io
+    import random
+    import numpy as np
+    import torch
+    mods = _import_reference()
+    if mods is None:
+        return {"unavailable": "baseline/_ref/code is missing"}
+    rg, ra, rr = mods
+    from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
+    net = AlphaNNet(input_shape=(2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0, backend="torch", dtype="fp32", device="cpu")
+    evals = [0]
+
+    class Shim:
+        def v(self, X):
+            evals[0] += len(X)
+            return net.v(np.array(X))
+    random.seed(0); np.random.seed(0)
+    gs = {i: rg.Game(i, SIDE, SIDE, SNAKES, HEALTH_DEC) for i in range(games)}
+    alice = ra.Agent(Shim(), 2, True, depth, breadth)
+    ids = [i for g in gs.values() for i in g.get_ids()]
+    t0 = time.time()
+    with contextlib.redirect_stdout(io.StringIO()):
+        alice.make_moves(gs, ids)
+    dt = time.time() - t0
+    sims = games * (breadth // 8) * 8
+    return {"sims_per_sec": sims / dt, "nn_evals_per_sec": evals[0] / dt, "cores": os.cpu_count() or 1, "torch_threads": torch.get_num_threads(),
+            "kind": "reference (unmodified utils/agent.py + utils/game.py) + torch-CPU fp32 network behind AlphaNNet.v",
+            "sample": "configs[0] bounded: %d games x breadth %d (%d sims/move), depth %d, one root turn, %.1f s" % (games, breadth, (breadth // 8) * 8, depth, dt)}
+
+
 def selfplay_api_leg(rank, games, breadth, depth, turns):
     """The same self-play loop through the reference-facing Python API (MPGameRunner.run + Agent.make_moves): host lists of
-    ids and moves, training records copied to the host every root turn (agent.py:93-97)."""
+    ids and moves; the training records (agent.py:93-97) stay in HBM (asz_records_append), only the moves cross PCIe."""
     import torch
     from alphasnake_zero_b200.utils.agent import Agent
     from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet
@@ -184,12 +267,16 @@ def selfplay_api_leg(rank, games, breadth, depth, turns):
     torch.cuda.synchronize()
     dt = time.time() - t0
     s1 = gr.engine.search_stats()
-    rec_bytes = (len(alice.records) - n0) * (PLANE_BYTES + 12)
+    n_rec = len(alice.records) - n0
+    t1 = time.time()
+    X, V, bs = alice.sample_training_batch()           # alpha_snake_zero_trainer.py:62-77, 93-100: sample + mirror, one gather kernel
+    torch.cuda.synchronize()
     return {"sims_per_sec": (s1["subgames"] - s0["subgames"]) / dt, "nn_evals_per_sec": (s1["evals"] - s0["evals"]) / dt,
-            "root_turns": turns, "seconds": dt, "records": len(alice.records) - n0,
-            "d2h_bytes_per_turn": rec_bytes / max(turns, 1) + games * 8 * 13, "h2d_bytes_per_turn": games * 8,
+            "root_turns": turns, "seconds": dt, "records": n_rec, "records_resident": "HBM (asz_records_append: one encode launch per turn)",
+            "d2h_bytes_per_turn": games * 8 + games * (SNAKES + 1 + 8), "h2d_bytes_per_turn": games * 8,
+            "training_batch": {"rows": int(X.shape[0]), "batch_size": bs, "seconds": time.time() - t1, "where": "device (asz_records_gather, mirrored)"},
             "api": "MPGameRunner(%d games).run(Agent(net, 2, True, %d, %d), max_turns=%d) after 32 uniform-random tics with in-place "
-                   "reset; host lists of ids and moves, training records copied to the host every root turn" % (games, depth, breadth, turns)}
+                   "reset; host lists of ids and moves; records and root Q stay on the device" % (games, depth, breadth, turns)}
 
 
 NET_FLOPS = {11: 1043724288, 19: 3240040448}   # per evaluation, 2 * MAC, convolutions + dense
@@ -251,9 +338,10 @@ def selfplay_leg(rank, games, breadth, depth, turns, warm, use_net=True, side=SI
     return out
 
 
-def cpu_selfplay_baseline(games=8, breadth=50, depth=8):
-    """configs[0] of BASELINE.json on the host cores, bounded: the C port of the reference's search with a torch-CPU fp32
-    network of identical architecture as AlphaNNet.v (TensorFlow is not installable here).  One root turn."""
+def cpu_selfplay_baseline(games=4, breadth=100, depth=8):
+    """The GPU self-play leg's own shape (configs[2]: breadth 100 = 96 sims/move, depth 8, base 2, games of every age) on the host
+    cores, bounded to a few games: the C port of the reference's search with a torch-CPU fp32 network of identical
+    architecture as AlphaNNet.v (TensorFlow is not installable here).  One root turn."""
     import numpy as np
     import torch
     from oracle import oracle as orc
@@ -262,14 +350,15 @@ def cpu_selfplay_baseline(games=8, breadth=50, depth=8):
     gs = []
     for gi in range(games):
         g = orc.OracleGame(SIDE, SIDE, SNAKES, HEALTH_DEC); g.init_native(0, gi, 0); g.set_ids(gi, 0); gs.append(g)
+    orc.env_run(games, SIDE, SIDE, SNAKES, HEALTH_DEC, CHANCE, 0, 32, encode=False, n_threads=1, games=gs)   # games of every age, like the GPU leg
     agent = orc.OracleAgent(base=2.0, training=True, max_depth=depth, max_breadth=breadth, value_fn=lambda X: net.v(np.array(X)))
     t0 = time.time()
     agent.make_moves(gs, games, root_turn=0, seed=0)
     dt = time.time() - t0
     return {"sims_per_sec": agent.stat("subgames") / dt, "node_visits_per_sec": agent.stat("node_visits") / dt,
             "nn_evals_per_sec": agent.stat("evals") / dt, "cores": os.cpu_count() or 1, "torch_threads": torch.get_num_threads(),
-            "kind": "port (C search) + torch-CPU fp32 network", "sample": "configs[0] bounded: %d games x breadth %d (%d sims/move), "
-            "depth %d, one root turn, %.1f s" % (games, breadth, (breadth // 8) * 8, depth, dt)}
+            "kind": "port (C search) + torch-CPU fp32 network", "sample": "configs[2] bounded: %d of 4096 games x breadth %d (%d sims/move), "
+            "depth %d, after 32 uniform-random tics, one root turn, %.1f s" % (games, breadth, (breadth // 8) * 8, depth, dt)}
 
 
 def run_reference(args, rank, world):
@@ -306,7 +395,8 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "u16/f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 11x11, 4 snakes, lockstep games, uniform-random actions, tic + fp32 plane encode",
                    "games_per_step": g, "tics_per_step": tics, "planes_per_step": planes / max(steps, 1)},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "python_reference": python_reference_env(4.0)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -340,16 +430,22 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]      # one event per launch: a slow regime shows
     barrier()
     ev0.record()
-    for _ in range(K):
+    step_ev[0].record()
+    for i in range(K):
         eng.step(**kw)
+        step_ev[i + 1].record()
     ev1.record()
     if rank == 0:
         sampler.sample_now()      # the K launches are queued and executing: a sample from this thread is inside the region
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    per_launch = np.array([step_ev[i].elapsed_time(step_ev[i + 1]) * 1e3 for i in range(K)])      # us, includes the 2 us memset
+    launch_us = {"p05": float(np.percentile(per_launch, 5)), "p50": float(np.median(per_launch)), "p95": float(np.percentile(per_launch, 95)),
+                 "max": float(per_launch.max()), "what": "CUDA events around every launch of the timed region (counter memset + kernel)"}
     t_after = eng.totals()
     steps_local = t_after["tics"] - t_before["tics"]
     planes_local = t_after["planes"] - t_before["planes"]
@@ -382,6 +478,33 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = e0.elapsed_time(e1)
     e2e_steps_local = eng.totals()["tics"] - t_b["tics"]
 
+    # what the headline e2e number does NOT do: ship the planes to the host.  The consumer of the planes is the value network on
+    # the same GPU; a caller that wants them in host memory pays PCIe for ~1 GB per step (reported once, rank 0, 3 steps).
+    planes_to_host = None
+    if rank == 0 and not args.no_selfplay:
+        try:
+            h_planes = torch.empty(GAMES * SNAKES, 2 * SIDE - 1, 2 * SIDE - 1, 3).pin_memory()
+            h_ids = torch.empty(GAMES * SNAKES, dtype=torch.int32).pin_memory()
+
+            def e2e_planes_step(i):
+                _lib.check(L.asz_env_step_host(eng.h, flags, _lib.SPAWN_NATIVE, C.c_void_p(act_pool[i % n_pool].data_ptr()), None,
+                                               C.c_void_p(h_ended.data_ptr()), C.c_void_p(h_rewards.data_ptr()), C.byref(rows),
+                                               C.c_void_p(h_planes.data_ptr()), C.c_void_p(h_ids.data_ptr()), eng.stream))
+            e2e_planes_step(0)
+            torch.cuda.synchronize()
+            tb = eng.totals()
+            t0 = time.time()
+            for i in range(3):
+                e2e_planes_step(i)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            planes_to_host = {"value": (eng.totals()["tics"] - tb["tics"]) / dt, "unit": UNIT, "d2h_bytes_per_step": int(rows.value) * PLANE_BYTES,
+                              "note": "asz_env_step_host with h_planes: every plane copied to pinned host memory (PCIe bound); not the "
+                                      "product path, shown so that nobody reads the e2e figure as including it"}
+            del h_planes, h_ids
+        except Exception as ex:
+            planes_to_host = {"error": repr(ex)}
+
     # ---- leg 3: self-play (search + value network) on every rank ------------------------------------------------------
     sp = {}
     if not args.no_selfplay:
@@ -410,24 +533,62 @@ def run_ours(args, rank, world, local_rank):
                 sp["mcts_e2e"] = {"error": repr(ex)}
 
     # ---- per-generation weight broadcast (the only collective of the design, outside the hot loop) ------
+    # Real weights through alphasnake_zero_b200.parallel: every rank starts from DIFFERENT random weights, rank 0's are pushed
+    # into every rank's live native network (asz_net_update_weights), a checksum proves all ranks hold the same bits and the
+    # network outputs agree; then the hand-off of a sampled training batch and of the log counters, all on device tensors.
     bcast = None
     if world > 1:
-        from alphasnake_zero_b200.utils.alpha_nnet import flatten_weights, init_weights
-        n_par = sum(a.size for a in flatten_weights(init_weights((2 * SIDE - 1, 2 * SIDE - 1, 3), seed=0)))
-        flat = torch.zeros(n_par, dtype=torch.float32, device=dev)
-        for _ in range(3):
-            dist.broadcast(flat, src=0)
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(10):
-            dist.broadcast(flat, src=0)
-        b1.record()
-        barrier()
-        t = torch.tensor([b0.elapsed_time(b1) / 10.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        bcast = {"bytes": int(n_par * 4), "ms": float(t[0]), "what": "torch.distributed.broadcast (NCCL) of all weights and BN "
-                 "buffers of the value network, once per generation, not inside any timed region above"}
+        from alphasnake_zero_b200 import parallel
+        from alphasnake_zero_b200.utils.alpha_nnet import AlphaNNet, flatten_weights
+        try:
+            net = AlphaNNet(input_shape=(2 * SIDE - 1, 2 * SIDE - 1, 3), seed=100 + rank, backend="native")
+            net._get_native()
+            differ_before = not parallel.weights_equal_all_ranks(net.weights)
+            for _ in range(2):
+                parallel.broadcast_weights(net, src=0)
+            barrier()
+            t0 = time.time()
+            parallel.broadcast_weights(net, src=0)
+            barrier()
+            whole_ms = (time.time() - t0) * 1e3
+            equal = parallel.weights_equal_all_ranks(net.weights)
+            # the device copies really changed: identical outputs on every rank for the same planes
+            gen = torch.Generator(device="cpu"); gen.manual_seed(7)
+            probe = torch.rand(64, 2 * SIDE - 1, 2 * SIDE - 1, 3, generator=gen).to(dev)
+            v = net.v_device(probe).double().sum().reshape(1)
+            vmin, vmax = v.clone(), v.clone()
+            dist.all_reduce(vmin, op=dist.ReduceOp.MIN); dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+            n_par = sum(a.size for a in flatten_weights(net.weights))
+            flat = torch.zeros(n_par, dtype=torch.float32, device=dev)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(10):
+                dist.broadcast(flat, src=0)
+            b1.record()
+            barrier()
+            t = torch.tensor([b0.elapsed_time(b1) / 10.0, whole_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            # sampled training batch: 5 x 2048 records drawn over the union of the ranks' stores, only those rows move
+            local_planes = torch.rand(20000, 2 * SIDE - 1, 2 * SIDE - 1, 3, device=dev)
+            local_values = torch.rand(20000, 3, device=dev)
+            barrier()
+            t0 = time.time()
+            X, V, bs = parallel.gather_sampled_batch(20000, lambda idx: (local_planes[idx.to(dev)], local_values[idx.to(dev)]),
+                                                     (2 * SIDE - 1, 2 * SIDE - 1, 3), dst=0)
+            barrier()
+            batch_ms = (time.time() - t0) * 1e3
+            counters = parallel.reduce_counters([1.0, 2.0, 3.0, 4.0, 5.0, 6.0], 1, dst=0)
+            bcast = {"bytes": int(n_par * 4), "ms": float(t[0]), "end_to_end_ms": float(t[1]),
+                     "weights_equal_all_ranks": bool(equal and differ_before), "outputs_equal_all_ranks": bool(float(vmin) == float(vmax)),
+                     "sampled_batch": {"rows": None if X is None else int(X.shape[0]), "batch_size": bs, "ms": batch_ms,
+                                       "what": "parallel.gather_sampled_batch: 5 x 2048 of 20,000 records per rank, tensor gather over NCCL"},
+                     "counters_reduced": counters == [1.0, 2.0, 3.0, 4.0, 5.0, 6.0] if counters is not None else None,
+                     "what": "parallel.broadcast_weights(AlphaNNet) over NCCL: rank 0's weights and BN buffers into every rank's live native "
+                             "network (asz_net_update_weights), once per generation, outside every timed region above; `ms` is the "
+                             "collective alone (device events), `end_to_end_ms` includes flattening, the host copy and the operand rebuild"}
+        except Exception as ex:
+            bcast = {"error": repr(ex)}
 
     # ---- reduce over ranks: max time, sum of work ----------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local)], dtype=torch.float64, device=dev)
@@ -467,15 +628,19 @@ def run_ours(args, rank, world, local_rank):
                                "native food spawn, in-place reset, tic + fp32 NHWC plane encode of every live snake" % GAMES,
                    "games_per_gpu": GAMES, "planes_per_step": planes_all / max(steps_all, 1),
                    "l2": "each launch writes %.0f MB of planes (> 126 MB L2); the 21 MB of game records may stay L2 resident"
-                         % (bytes_per_launch / 1e6)},
+                         % (bytes_per_launch / 1e6),
+                   "plane_layout": "fp32 NHWC rows, 5,312 B apart (asz_plane_pitch: 5,292 B plane + 20 B pad, 32-byte aligned rows)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "env_step_kernel<11,8>", "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bytes_per_launch},
+                     "traffic": traffic, "kernel": "env_step_kernel (pitched rows, warp_encode_game_v3b)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "note": "algorithmic bytes count 5,292 B per plane; the kernel writes 5,312 B (rows padded to 32-byte sectors)"},
         "e2e": {"value": e2e_steps_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": GAMES * 8,
                 "d2h_bytes_per_step": GAMES + GAMES * 8 + 4,
                 "note": "asz_env_step_host: pinned host actions in, per-game ended/rewards + row count out; planes stay in HBM for the network"},
-        "gpu_launches": K, "clocks": clocks,
+        "gpu_launches": K, "clocks": clocks, "launch_us": launch_us,
     }
+    if planes_to_host is not None:
+        out["e2e_planes_to_host"] = planes_to_host
     out.update(sp)
     if rank_ms is not None:   # ms per step of every rank: the aggregate above is paced by the slowest one
         out["rank_ms_per_step"] = rank_ms
@@ -483,11 +648,19 @@ def run_ours(args, rank, world, local_rank):
         out["weight_broadcast"] = bcast
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
+        try:      # the reference's own Python next to its C port
+            out["cpu_baseline"]["python_reference"] = python_reference_env()
+        except Exception as ex:
+            out["cpu_baseline"]["python_reference"] = {"error": repr(ex)}
         if not args.no_selfplay:
             try:
                 out["mcts_cpu_baseline"] = cpu_selfplay_baseline()
             except Exception as ex:
                 out["mcts_cpu_baseline"] = {"error": repr(ex)}
+            try:
+                out["mcts_cpu_baseline"]["python_reference"] = python_reference_selfplay()
+            except Exception as ex:
+                out["mcts_cpu_baseline"]["python_reference"] = {"error": repr(ex)}
     emit(out)
     if world > 1:
         dist.destroy_process_group()
