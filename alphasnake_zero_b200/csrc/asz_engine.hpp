@@ -75,6 +75,23 @@ struct asz_engine {
   int8_t* rewards = nullptr;      // [G*8]
   unsigned long long* totals = nullptr;  // [8]
   int device_hints = 1, host_hints = 0, step_hints = 1;   // L2 policy hints of env_step_kernel (asz_env.cu)
+  // The fused tic + encode kernel of a large engine streams ~1 GB per launch through the L2 and is 1.5x slower when the L2 is full
+  // of dirty lines (asz_env.cu, "L2 conditioning").  The engine knows when its own work has dirtied the L2 (bulk initialisation,
+  // encode-only launches, the search and the network in between) and runs the read sweep before the next tic + encode launch.
+  bool l2_dirty = true;
+  int auto_condition = 1;          // ASZ_AUTO_CONDITION=0 disables (experiments)
+  // ... and because a sweep does not always take (and other kernels of the application dirty the L2 behind the engine's back) it
+  // MEASURES: every 16th streaming launch is bracketed by two events and its row count is copied to a pinned word; when the
+  // sample shows the slow regime (plane bytes / time below l2_slow_gbs) the next launch is preceded by another sweep.
+  struct L2Monitor {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int32_t* h_rows = nullptr;     // pinned
+    bool pending = false;
+    int since_sample = 0, fails = 0, cooldown = 0;
+    unsigned long long sweeps = 0, samples = 0, slow_samples = 0;
+    double last_gbs = 0.0;
+  } l2mon;
+  double l2_slow_gbs = 5500.0;     // ASZ_L2_SLOW_GBS: between the two regimes of a B200 (about 4,400 and 6,600 GB/s of plane bytes)
   asz::SearchState* search = nullptr;
   asz::RecordStore* records = nullptr;   // device-resident training records (asz_records_*)
 };

@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   __syncthreads();
   EncodeCtx<G> ctx;
   EncodeCtxP<G> ctxp;
-  ctxp.cur = stage0; ctxp.oth = stage0 + SM::WSTAGE; ctxp.seam = s_bg; ctxp.policy = HINTS ? l2_policy_evict_first() : 0ull;
+  // p.hints (experiments): 1 = both policies, 2 = planes evict_first only, 3 = records evict_last only
+  ctxp.cur = stage0; ctxp.oth = stage0 + SM::WSTAGE; ctxp.seam = s_bg;
+  ctxp.policy = HINTS ? (p.hints == 3 ? l2_policy_evict_normal() : l2_policy_evict_first()) : 0ull;
   ctxp.lin = reinterpret_cast<const int16_t*>(s_plut);
   ctxp.hv = reinterpret_cast<const float*>(s_plut + PitchLut<G>::LIN * 2);
   ctxp.food = ctxp.hv + PitchLut<G>::HV;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   constexpr bool given_actions = ACTS;
   int act_slot = 0;
   int g = (int)blockIdx.x * WARPS + warp;
-  const uint64_t keep = HINTS ? l2_policy_evict_last() : 0ull;
+  const uint64_t keep = HINTS ? (p.hints == 2 ? l2_policy_evict_normal() : l2_policy_evict_last()) : 0ull;
   auto prefetch = [&](int gi) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cells + (size_t)gi * G::PC);
     if constexpr (HINTS) {
@@ -354,6 +356,24 @@ __global__ void __launch_bounds__(WARPS * 32) env_reset_kernel(uint16_t* cells, 
   store_meta(meta + (size_t)g * 8, m, lane);
 }
 
+// ---- L2 conditioning ------------------------------------------------------------------------------------------------
+// env_step_kernel streams ~1 GB of planes per launch through a 126 MB L2 and runs in one of two stable regimes:
+// ~150 us per launch when the L2's normal-priority lines are CLEAN (the evict_first plane lines then form a small pool that
+// is written back as fast as it is filled), ~220 us when the L2 is full of dirty lines (after bulk initialisation, after
+// another kernel streamed writes through it, after encode-only launches, whose store rate exceeds what HBM drains).  The L2
+// does not clean itself when idle; reading more than ~8x its capacity does.  This kernel is that read sweep.
+__global__ void __launch_bounds__(256) l2_sweep_kernel(const uint4* __restrict__ p, size_t n, int passes, unsigned long long* sink) {
+  unsigned long long acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int k = 0; k < passes; ++k)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      uint4 v;
+      asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + i));   // volatile asm: every pass loads
+      acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x9E3779B97F4A7C15ull) *sink = acc;     // never true in practice; keeps the loads alive
+}
+
 template <int SIDE>
 struct EnvLaunch {
 #ifndef ASZ_ENV_WARPS       // occupancy experiments (tools/env_profile.py build-variant NAME -DASZ_ENV_WARPS=.. -DASZ_ENV_MINB=..)
@@ -449,7 +469,12 @@ int asz_version(void) { return ASZ_VERSION; }
 static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   e->cfg = *cfg;
   { const char* v = getenv("ASZ_ENV_HINTS"); e->device_hints = v ? atoi(v) : 1; }            // experiments only
-  { const char* v = getenv("ASZ_ENV_HINTS_HOST"); e->host_hints = v ? atoi(v) : 0; }
+  { const char* v = getenv("ASZ_ENV_HINTS_HOST"); e->host_hints = v ? atoi(v) : 1; }
+  { const char* v = getenv("ASZ_AUTO_CONDITION"); e->auto_condition = v ? atoi(v) : 1; }
+  { const char* v = getenv("ASZ_L2_SLOW_GBS"); if (v) e->l2_slow_gbs = atof(v); }
+  ASZ_CUDA(cudaEventCreate(&e->l2mon.ev0));
+  ASZ_CUDA(cudaEventCreate(&e->l2mon.ev1));
+  ASZ_CUDA(cudaMallocHost(&e->l2mon.h_rows, sizeof(int32_t)));
   e->step_hints = e->device_hints;
   ASZ_CUDA(cudaGetDevice(&e->device));
   ASZ_CUDA(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, e->device));
@@ -507,6 +532,9 @@ int asz_engine_destroy(asz_engine* e) {
   search_destroy(e);
   records_destroy(e);
   gameset_free(e->root);
+  if (e->l2mon.ev0) cudaEventDestroy(e->l2mon.ev0);
+  if (e->l2mon.ev1) cudaEventDestroy(e->l2mon.ev1);
+  if (e->l2mon.h_rows) cudaFreeHost(e->l2mon.h_rows);
   cudaFree(e->planes); cudaFree(e->row_ids); cudaFree(e->row_count); cudaFree(e->actions); cudaFree(e->spawn_cells);
   cudaFree(e->ended); cudaFree(e->rewards); cudaFree(e->totals);
   delete e;
@@ -517,6 +545,7 @@ int asz_reset(asz_engine* e, void* stream) {
   if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  e->l2_dirty = true;      // bulk initialisation (and usually the caller's allocation of the batch buffer) leaves the L2 dirty
   ASZ_CUDA(cudaMemsetAsync(e->totals, 0, 32 * sizeof(unsigned long long), st));
   switch (e->cfg.side) {
     case 7: return EnvLaunch<7>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
@@ -557,6 +586,40 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals; p.prof = e->totals + 16;
   p.sched = reinterpret_cast<unsigned long long*>(e->row_count);   // low word = e->row_count[0]: the row count the callers read
   p.hints = e->step_hints;
+  // "L2 conditioning": streaming launches (tic + encode into pitched rows of an engine whose batch is much larger than the L2)
+  const bool streaming = (a->flags & ASZ_STEP_TIC) && (a->flags & ASZ_STEP_ENCODE) && p.pitched && e->auto_condition &&
+                         (size_t)e->cfg.games * e->cfg.snakes * e->pitch * sizeof(float) >= ((size_t)192 << 20);
+  asz_engine::L2Monitor& mon = e->l2mon;
+  bool sample = false;
+  if (streaming) {
+    if (mon.pending && cudaEventQuery(mon.ev1) == cudaSuccess) {       // an earlier sample has finished: which regime was it in?
+      float ms = 0.0f;
+      mon.pending = false;
+      if (cudaEventElapsedTime(&ms, mon.ev0, mon.ev1) == cudaSuccess && ms > 0.0f) {
+        const double bytes = (double)*mon.h_rows * e->pitch * sizeof(float);
+        if (bytes >= (double)((size_t)192 << 20)) {
+          mon.last_gbs = bytes / (ms * 1e-3) / 1e9;
+          mon.samples += 1;
+          if (mon.last_gbs < e->l2_slow_gbs) { mon.slow_samples += 1; mon.fails += 1; e->l2_dirty = true; }
+          else mon.fails = 0;
+        }
+      }
+    }
+    cudaGetLastError();                                                 // cudaErrorNotReady of the query is not an error
+    if (mon.cooldown > 0) mon.cooldown -= 1;
+    if (e->l2_dirty && mon.cooldown == 0) {
+      if (mon.fails >= 4) { mon.cooldown = 4096; mon.fails = 0; e->l2_dirty = false; }   // sweeps do not take here: stop trying for a while
+      else {
+        const int rc0 = asz_condition_l2(e, stream);
+        if (rc0 != ASZ_OK) return rc0;
+        mon.sweeps += 1;
+        mon.since_sample = 12;                                          // look at the result soon
+      }
+    }
+    if (!mon.pending && ++mon.since_sample >= 16) { sample = true; mon.since_sample = 0; }
+  }
+  if ((a->flags & ASZ_STEP_ENCODE) && !(a->flags & ASZ_STEP_TIC)) e->l2_dirty = true;   // encode-only launches out-run the HBM drain
+  if (sample) ASZ_CUDA(cudaEventRecord(mon.ev0, st));
   ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, (kWorkCounterAt + 32) * sizeof(int32_t), st));
   int rc;
   switch (e->cfg.side) {
@@ -565,6 +628,11 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
     default: rc = EnvLaunch<19>::step(p, st); break;
   }
   if (rc != ASZ_OK) return rc;
+  if (sample) {
+    ASZ_CUDA(cudaMemcpyAsync(mon.h_rows, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ASZ_CUDA(cudaEventRecord(mon.ev1, st));
+    mon.pending = true;
+  }
   if (a->d_row_count && a->d_row_count != e->row_count)
     ASZ_CUDA(cudaMemcpyAsync(a->d_row_count, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return ASZ_OK;
@@ -626,11 +694,27 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
   return ASZ_OK;
 }
 
+int asz_condition_l2(asz_engine* e, void* stream) {
+  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
+  const size_t bytes = (size_t)e->cfg.games * e->cfg.snakes * e->pitch * sizeof(float);
+  e->l2_dirty = false;
+  if (bytes < ((size_t)192 << 20)) return ASZ_OK;      // a batch that fits the L2 does not stream through it: nothing to condition
+  const size_t want = (size_t)5 << 28;                 // 1.25 GB of read traffic (8x the L2 is what the experiments needed)
+  const int passes = (int)((want + bytes - 1) / bytes);
+  l2_sweep_kernel<<<e->n_sm * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(e->planes), bytes / 16, passes, e->totals + 31);
+  if (!cuda_ok(cudaGetLastError(), "l2_sweep_kernel")) return ASZ_ERR_CUDA;
+  e->l2_dirty = false;
+  return ASZ_OK;
+}
+
 int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
   if (!e || !h_totals) { set_error("null argument"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
   ASZ_CUDA(cudaDeviceSynchronize());
   ASZ_CUDA(cudaMemcpy(h_totals, e->totals, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  h_totals[9] = e->l2mon.sweeps; h_totals[10] = e->l2mon.samples; h_totals[11] = e->l2mon.slow_samples;   // host-side: L2 monitor
+  h_totals[12] = (uint64_t)e->l2mon.last_gbs;
   return ASZ_OK;
 }
 

@@ -133,11 +133,16 @@ class Engine:
         a.d_rewards = self.rewards.data_ptr()
         check(self.L.asz_env_step(self.h, C.byref(a), self.stream))
 
+    def condition_l2(self):
+        """one read sweep that leaves the L2 full of clean lines: the fast regime of the fused tic + encode kernel on engines whose
+        batch is much larger than the L2 (asz_condition_l2; a no-op for small engines)"""
+        check(self.L.asz_condition_l2(self.h, self.stream))
+
     def totals(self):
         t = np.zeros(16, np.uint64)
         check(self.L.asz_get_totals(self.h, _np(t)))
-        return dict(zip(("wall", "body", "head", "starve", "food_eaten", "game_length", "episodes", "tics", "planes"),
-                        t.tolist()))
+        return dict(zip(("wall", "body", "head", "starve", "food_eaten", "game_length", "episodes", "tics", "planes",
+                         "l2_sweeps", "l2_samples", "l2_slow_samples", "l2_last_gbs"), t.tolist()))
 
     # ---- convenience used by tests and the drop-in classes -------------------------------------------------------
     def rows(self):
