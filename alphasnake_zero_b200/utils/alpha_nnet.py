@@ -193,14 +193,22 @@ class AlphaNNet:
         self._native = None
 
     def save(self, name):
-        """alpha_nnet.py:108-109 writes models/<name>.h5; h5py is not available here, so the same Keras-ordered
-        weight list is stored as models/<name>.npz (SURVEY.md 8(f) #3)."""
+        """alpha_nnet.py:108-109: models/<name>.h5 in the layout of tf.keras 2.2.4's Model.save (written by the pure-NumPy HDF5 subset
+        of utils/h5lite.py: no h5py needed), plus the same Keras-ordered weight list as models/<name>.npz (SURVEY.md 8(f) #3)."""
         import os
+        from . import keras_h5
         os.makedirs("models", exist_ok=True)
+        keras_h5.save(self.weights, "models/" + name + ".h5")
         np.savez("models/" + name + ".npz", side=self.weights["side"], *flatten_weights(self.weights))
 
 
 def load_weights(path):
+    """alpha_nnet.py:11-12: `model_name` is a path; a Keras .h5 model file (what the reference's train.py passes:
+    "models/<name><generation>.h5"), an .npz written by save(), or a path without extension (.npz first, then .h5)."""
+    import os
+    if path.endswith(".h5") or (not path.endswith(".npz") and not os.path.exists(path + ".npz") and os.path.exists(path + ".h5")):
+        from . import keras_h5
+        return keras_h5.load(path if path.endswith(".h5") else path + ".h5")
     z = np.load(path if path.endswith(".npz") else path + ".npz")
     arrs = [z["arr_%d" % i] for i in range(len(z.files) - 1)]
     side = int(z["side"])

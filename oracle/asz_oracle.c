@@ -486,6 +486,8 @@ struct oagent {
   oentry **tab; size_t cap, n;   /* open addressing over pointers: entries never move */
   uint64_t stats[8];
   uint64_t alias_errors;
+  int rhat_before_backups;   /* 0 = reference (agent.py:214: Q_row is a live alias), 1 = every r-hat of a step from the values before the
+                                step's backups (what a parallel implementation computes); see oa_set_rhat_mode */
   /* records */
   float *rec_planes; float *rec_q; int n_rec, cap_rec, plane_len;
 };
@@ -563,6 +565,12 @@ int oa_table_dump(const oagent *a, int cap, uint64_t *keys, float *Q, float *Wt,
   }
   return n;
 }
+/* The reference computes r-hat = pmf . Q_row row by row inside the backup loop, and Q_row aliases the live table entry
+ * (agent.py:180,214): when a row's current state is an ancestor on the path of an EARLIER row of the same step, it sees that
+ * row's backup.  mode 1 computes every r-hat of a step before any backup of the step (the order-free definition the CUDA
+ * kernels implement); it exists so that tests can separate this one documented deviation from everything else. */
+void oa_set_rhat_mode(oagent *a, int before_backups) { a->rhat_before_backups = before_backups ? 1 : 0; }
+
 uint64_t oa_stat(const oagent *a, int which) { return which == 7 ? a->alias_errors : a->stats[which & 7]; }
 int oa_n_records(const oagent *a) { return a->n_rec; }
 void oa_get_record(const oagent *a, int i, float *plane, float *q) {
@@ -682,10 +690,18 @@ int oa_make_moves(oagent *a, ogame **games, int n_games, oa_trace *tr, int *move
         }
       }
       /* agent.py:208-222 */
+      if (a->rhat_before_backups) {     /* not the reference: all estimates first (row_pmf[3r] is reused to carry r-hat) */
+        for (int r = 0; r < n_rows; ++r) {
+          float *pm = row_pmf + 3 * r; const float *q = row_e[r]->Q;
+          float est = pm[0] * q[0]; est = est + pm[1] * q[1]; est = est + pm[2] * q[2];
+          pm[0] = est;
+        }
+      }
       for (int r = 0; r < n_rows; ++r) {
         opath *p = &paths[row_sub[r] * S + row_snake[r]];
         const float *pm = row_pmf + 3 * r; const float *q = row_e[r]->Q;   /* live alias (agent.py:180,214) */
         float est = pm[0] * q[0]; est = est + pm[1] * q[1]; est = est + pm[2] * q[2];
+        if (a->rhat_before_backups) est = pm[0];
         backup(p, est);
         if (p->n >= max_path) { fprintf(stderr, "oa_make_moves: path overflow\n"); abort(); }
         p->e[p->n] = row_e[r]; p->mv[p->n] = row_mv[r]; p->n += 1;

@@ -81,6 +81,7 @@ typedef void (*og_value_fn)(void *ctx, const float *planes, int n, int H, int W,
 oagent *oa_new(double softmax_base, int training, int max_depth, int max_breadth, og_value_fn fn, void *ctx);
 void oa_free(oagent *a);
 void oa_clear(oagent *a);
+void oa_set_rhat_mode(oagent *a, int before_backups);   /* 0 = reference order (default), 1 = all r-hat before the step's backups */
 /* trace: one u8 per (epoch, step, subgame, snake id): in replay mode read, in native mode written.
  * Layout: moves[((epoch*max_steps + step)*n_sub_abs + abs_sub)*S + snake], 255 = no row.  root_moves[n_rows].
  * mode 0: sample with Philox(seed; root_turn, epoch, step, abs_sub, snake); mode 1: replay from the trace. */

@@ -63,6 +63,7 @@ def lib():
         L.oenv_run.argtypes = [vp, i32, i32, i32, i32, i32, u32, u64, i32, i32, i32, C.POINTER(EnvStats)]
         L.oa_new.restype = vp; L.oa_new.argtypes = [C.c_double, i32, i32, i32, vp, vp]
         L.oa_free.argtypes = [vp]; L.oa_clear.argtypes = [vp]
+        L.oa_set_rhat_mode.argtypes = [vp, i32]
         L.oa_make_moves.restype = i32; L.oa_make_moves.argtypes = [vp, vp, i32, C.POINTER(Trace), vp, vp]
         L.oa_table_size.restype = i32; L.oa_table_size.argtypes = [vp]
         L.oa_table_dump.restype = i32; L.oa_table_dump.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -235,6 +236,11 @@ class OracleAgent:
 
     def clear(self):
         lib().oa_clear(self.h)
+
+    def set_rhat_mode(self, before_backups):
+        """False (default) = the reference's order: r-hat of a row is computed inside the backup loop from a live alias of the
+        table entry (agent.py:180,214); True = every r-hat of a step from the values before the step's backups."""
+        lib().oa_set_rhat_mode(self.h, int(bool(before_backups)))
 
     def make_moves(self, games, total_games, root_turn=0, seed=0, tree_moves=None, root_moves=None, replay=False):
         """games: list of live OracleGame (their game_id must be set).  tree_moves: uint8 array

@@ -47,9 +47,11 @@ def test_one_generation_and_a_pit(tmp_path, monkeypatch):
     new = new.copy_and_compile()                                          # :83
     after = new.v(X[:32])
     assert np.isfinite(after).all() and np.abs(after - before).max() > 1e-4        # the weights moved
-    new.save("Test1")                                                     # :91 -> models/Test1 (npz instead of h5)
-    loaded = AlphaNNet(model_name="models/Test1")
+    new.save("Test1")                                                     # :91 -> models/Test1.h5 (Keras layout, utils/h5lite.py)
+    assert os.path.exists("models/Test1.h5")
+    loaded = AlphaNNet(model_name="models/Test1.h5")                      # train.py:35 passes "models/<name><generation>.h5"
     np.testing.assert_allclose(loaded.v(X[:32]), after, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(AlphaNNet(model_name="models/Test1").v(X[:32]), after, rtol=0, atol=1e-6)
     # pit.py:28-35: the new generation (snake ids 0..1) against the old one, 2 vs 2
     A, B = pit_agent.Agent(loaded), pit_agent.Agent(nnet)
     winners = pit_mp_game_runner.MPGameRunner(11, 11, 4, 9, 24).run(A, B, 2)

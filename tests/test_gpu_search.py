@@ -128,16 +128,19 @@ def test_native_search_with_compaction_inside_a_turn():
     (11, 4, 384, 8, 200, 2, 0, 12, 0),
     (19, 8, 16, 8, 400, 12, 20, 40, 1)])
 def test_native_search_at_baseline_config_shapes(side, S, G, D, breadth, turns, table_log2, warm, compactions):
-    # Q tolerance: at these sizes the same state often is the current node of one row and an ancestor on the path of an earlier row
-    # of the same step.  The reference's `Q_row` then aliases an entry that the earlier row's backup has already updated
-    # (agent.py:180,208-220: a sequential loop), while the kernels compute every r-hat of a step from the values before the step's
-    # backups.  Visit counts, keys, ages and sampled moves are unaffected (exact below); Q moves in the fifth digit.
-    n = _native_search_against_oracle(side, S, G, D, breadth, 2.0, True, turns, table_log2, warm_tics=warm, dump_every=97, q_atol=3e-4)
+    # At these sizes the same state often is the current node of one row and an ancestor on the path of an EARLIER row of the same
+    # step.  The reference's `Q_row` then aliases an entry the earlier row's backup has already updated (agent.py:180,208-220 is a
+    # sequential loop), while the kernels compute every r-hat of a step from the values before the step's backups.  The oracle can
+    # do either (OracleAgent.set_rhat_mode): against the order-free mode the engine must match to float reassociation at full
+    # size; the distance between the oracle's two modes (visit counts, keys, ages, moves identical; a few Q values moving in the
+    # fourth digit) is what tests/test_oracle_mcts.py::test_rhat_order_modes measures.
+    n = _native_search_against_oracle(side, S, G, D, breadth, 2.0, True, turns, table_log2, warm_tics=warm, dump_every=97,
+                                      q_atol=2e-5, rhat_before=True)
     assert n >= compactions, "expected at least %d table compactions, saw %d" % (compactions, n)
 
 
 def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns, table_log2, sync_steps=False, want_mid=False,
-                                  warm_tics=0, dump_every=5, q_atol=5e-6):
+                                  warm_tics=0, dump_every=5, q_atol=5e-6, rhat_before=False):
     import os
     import torch
     from oracle import oracle as orc
@@ -159,6 +162,7 @@ def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns,
         live_counts = [g.n_live for g in games]
         assert min(live_counts) >= 2 and len(set(live_counts)) > 1        # running games with different numbers of snakes
     agent = orc.OracleAgent(base=base, training=training, max_depth=D, max_breadth=breadth)
+    agent.set_rhat_mode(rhat_before)
     done = [False] * G
     compactions, last_occupied, last_inserts = 0, 0, 0
     for t in range(turns):
@@ -183,7 +187,7 @@ def _native_search_against_oracle(side, S, G, D, breadth, base, training, turns,
         assert np.array_equal(tab["N"], otab["N"][oo]), "visit counts differ at turn %d" % t
         assert np.array_equal(tab["age"], otab["age"][oo])
         assert np.all(np.abs(tab["W"] - otab["W"][oo]) <= 1e-4 + (q_atol if q_atol > 5e-6 else 0.0) * tab["N"]), \
-            "W differs by %g" % np.abs(tab["W"] - otab["W"][oo]).max()
+            "W differs by %g" % np.abs(tab["W"] - otab["W"][oo]).max()     # float sums in a different order: error grows with N
         st = eng.search_stats()
         assert st["evals"] == agent.stat("evals") and st["node_visits"] == agent.stat("node_visits")
         assert st["subgame_tics"] == agent.stat("subgame_tics") and st["subgames"] == agent.stat("subgames")
