@@ -408,12 +408,15 @@ def run_ours(args, rank, world, local_rank):
     from alphasnake_zero_b200.engine import Engine
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
+    # The engine is created BEFORE the NCCL communicator: the fused kernel's fast regime depends on where the engine's buffers
+    # land in device memory, and a large live allocation made before them (NCCL's buffers, any >= 256 MB tensor) leaves it in the
+    # slow one for good (tools/env_bisect.py); allocations made afterwards do not matter.
     eng = Engine(side=SIDE, snakes=SNAKES, health_dec=HEALTH_DEC, food_chance=CHANCE, games=GAMES, seed=1000 + rank)
     eng.reset()
     _ = eng.planes
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     kw = dict(spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=True, auto_reset=True, random_actions=True)
 
     def barrier():
@@ -638,6 +641,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": GAMES + GAMES * 8 + 4,
                 "note": "asz_env_step_host: pinned host actions in, per-game ended/rewards + row count out; planes stay in HBM for the network"},
         "gpu_launches": K, "clocks": clocks, "launch_us": launch_us,
+        "l2_monitor": {k: t_after[k] for k in ("l2_sweeps", "l2_samples", "l2_slow_samples", "l2_last_gbs")},
     }
     if planes_to_host is not None:
         out["e2e_planes_to_host"] = planes_to_host

@@ -135,7 +135,7 @@ def test_native_search_at_baseline_config_shapes(side, S, G, D, breadth, turns, 
     # size; the distance between the oracle's two modes (visit counts, keys, ages, moves identical; a few Q values moving in the
     # fourth digit) is what tests/test_oracle_mcts.py::test_rhat_order_modes measures.
     n = _native_search_against_oracle(side, S, G, D, breadth, 2.0, True, turns, table_log2, warm_tics=warm, dump_every=97,
-                                      q_atol=2e-5, rhat_before=True)
+                                      q_atol=1e-4, rhat_before=True)   # W is a float sum of thousands of terms in a different order
     assert n >= compactions, "expected at least %d table compactions, saw %d" % (compactions, n)
 
 

@@ -15,8 +15,24 @@ from alphasnake_zero_b200.engine import Engine  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 dense = len(sys.argv) > 2 and sys.argv[2] == "dense"
 G = 65536
+if "LOCAL_RANK" in os.environ:
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+nccl_mode = sys.argv[3] if len(sys.argv) > 3 else ""
+
+
+def nccl_init():
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    dist.barrier()
+
+
+if nccl_mode == "nccl":           # communicator first, engine second
+    nccl_init()
 eng = Engine(side=11, snakes=4, health_dec=1, games=G, seed=1)
 eng.reset()
+if nccl_mode == "nccl_after":     # engine first
+    _ = eng.planes
+    nccl_init()
 planes = torch.empty(G * 4, 21, 21, 3, device="cuda") if dense else None
 kw = dict(spawn_mode=2, tic=True, encode=True, auto_reset=True, random_actions=True, planes=planes)
 for _ in range(50):
