@@ -68,7 +68,15 @@ struct asz_engine {
   // env-step scratch owned by the engine
   float* planes = nullptr;        // [G*S][pitch]
   int32_t* row_ids = nullptr;     // [G*S]
-  int32_t* row_count = nullptr;   // [1]
+  int32_t* row_count = nullptr;   // 8 MB of candidate locations for the kernel's one hot word (rows | game scheduler), see sched_off
+  // Where inside that buffer the hot 64-bit word currently lives.  65,536 returning atomics per launch go to this one address, and
+  // which L2 slice it is homed in decides whether the fused kernel can reach its fast regime at all: about half of the candidate
+  // addresses leave it at ~240 us per launch whatever the state of the L2 (tools/env_bisect.py).  The physical
+  // placement is not under the engine's control, so the L2 monitor rotates to the next candidate when sweeps do not help.
+  size_t sched_off = 0;
+  bool host_step = false;           // inside asz_env_step_host: results go to pinned host memory over PCIe, the launch is not judged
+  bool hot_word_selected = false;   // asz_reset's probe has chosen sched_off for this process
+  int32_t* rows_ptr() const { return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(row_count) + sched_off); }
   uint8_t* actions = nullptr;     // [G*8]
   int32_t* spawn_cells = nullptr; // [G]
   uint8_t* ended = nullptr;       // [G]
@@ -86,9 +94,10 @@ struct asz_engine {
   struct L2Monitor {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int32_t* h_rows = nullptr;     // pinned
-    bool pending = false;
+    bool pending = false, pending_host = false;
     int since_sample = 0, fails = 0, cooldown = 0;
-    unsigned long long sweeps = 0, samples = 0, slow_samples = 0;
+    unsigned long long sweeps = 0, samples = 0, slow_samples = 0, rotations = 0;
+    int candidate = 0;
     double last_gbs = 0.0;
   } l2mon;
   double l2_slow_gbs = 5500.0;     // ASZ_L2_SLOW_GBS: between the two regimes of a B200 (about 4,400 and 6,600 GB/s of plane bytes)

@@ -1,10 +1,16 @@
 // asz_env.cu -- lockstep Battlesnake tic with the plane encoding fused in, plus the env part of the C ABI.
 //
-// Kernel: one warp per game, WARPS games per CTA.  Per launch a warp loads its game record (cells + snakes + meta,
-// ~320 B at 11x11x4), steps it in shared memory (asz_game.cuh), writes the record back, and streams the plane of
-// every surviving snake (5,292 B each at 11x11) straight into the network's input batch with 16-byte stores.
-// Rows of the batch are handed out by one atomicAdd per CTA after a block-level scan of the live counts.
-// Roofline: HBM write bandwidth (planes are > 95 % of the bytes).
+// Kernel (env_step_kernel): persistent, 3 CTAs x 8 warps per SM, one warp = one game at a time.  A warp loads its game record
+// (cells + snakes + meta, ~350 B at 11x11x4; prefetched one game ahead), steps it in shared memory (asz_game.cuh: warp_tic),
+// writes the record back, takes its rows of the batch AND its next game with ONE 64-bit atomicAdd, and encodes the plane of
+// every surviving snake (5,292 B each at 11x11) into the network's input batch: the cells are scattered into a staged window
+// in shared memory and the copy engine (cp.async.bulk shared -> global) writes the plane, wall runs from a constant buffer.
+//   pitched rows (the engine's own buffers, asz_plane_pitch): planes start on 32-byte sectors, a game's planes are one
+//     sequence of bulk copies (warp_encode_game_v3b), no per-plane edge handling;
+//   dense rows (a caller's [rows][N][N][3] tensor): warp_encode_v2, three copies per plane + edge floats by single lanes.
+// Roofline: HBM write bandwidth (planes are > 95 % of the bytes).  The kernel has two timing regimes that
+// depend on the state of the L2 and on where its one hot word lives; "L2 conditioning" below and the monitor in asz_env_step
+// keep it in the fast one.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -437,10 +443,21 @@ struct EnvLaunch {
   }
 };
 
+// experiments (tools/env_bisect.py): ASZ_DEBUG_PAD="<index>:<MB>" inserts a dummy allocation before the index-th allocation of an engine
+static void debug_pad(int index) {
+  static int want = -2, mb = 0, seen_root = 0;
+  if (want == -2) { const char* v = getenv("ASZ_DEBUG_PAD"); want = -1; if (v) sscanf(v, "%d:%d", &want, &mb); }
+  (void)seen_root;
+  if (index == want && mb > 0) { void* p = nullptr; cudaMalloc(&p, (size_t)mb << 20); fprintf(stderr, "[asz] debug pad of %d MB before allocation %d\n", mb, index); }
+}
+
 int gameset_alloc(GameSet& gs, int n, int pc) {
   gs.n = n;
+  debug_pad(0);
   ASZ_CUDA(cudaMalloc(&gs.cells, (size_t)n * pc * sizeof(uint16_t)));
+  debug_pad(1);
   ASZ_CUDA(cudaMalloc(&gs.snakes, (size_t)n * 8 * sizeof(uint64_t)));
+  debug_pad(2);
   ASZ_CUDA(cudaMalloc(&gs.meta, (size_t)n * 8 * sizeof(uint32_t)));
   ASZ_CUDA(cudaMemset(gs.cells, 0, (size_t)n * pc * sizeof(uint16_t)));
   ASZ_CUDA(cudaMemset(gs.snakes, 0, (size_t)n * 8 * sizeof(uint64_t)));
@@ -455,6 +472,14 @@ void gameset_free(GameSet& gs) {
 constexpr int kWorkCounterAt = 320;   // ints
 
 static int pc_of(int side) { return side == 7 ? Geo<7>::PC : side == 11 ? Geo<11>::PC : Geo<19>::PC; }
+
+// k-th candidate address (byte offset in the 8 MB counter buffer) of the kernel's hot word: other address bits 7..22 every time
+static size_t hot_word_offset(int k) {
+  return ((size_t)k * 4096 + (size_t)(k % 29) * 128 + (size_t)(k % 3) * ((size_t)1 << 21)) % (((size_t)8 << 20) - 128);
+}
+static bool streams_through_l2(const asz_engine* e) {
+  return e->auto_condition && (size_t)e->cfg.games * e->cfg.snakes * e->pitch * sizeof(float) >= ((size_t)192 << 20);
+}
 
 }  // namespace asz
 
@@ -487,14 +512,19 @@ static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   const size_t G = (size_t)cfg->games, rows = G * (size_t)cfg->snakes;
   int rc = gameset_alloc(e->root, cfg->games, e->pc);
   if (rc != ASZ_OK) return rc;
+  debug_pad(3);
   ASZ_CUDA(cudaMalloc(&e->planes, rows * (size_t)e->pitch * sizeof(float) + 32));
+  debug_pad(4);
   ASZ_CUDA(cudaMalloc(&e->row_ids, rows * sizeof(int32_t)));
+  debug_pad(5);
   // one 64-bit word: [0] rows of the last step, [1] the kernel's game scheduler (EnvParams::sched); the rest is padding
-  ASZ_CUDA(cudaMalloc(&e->row_count, (kWorkCounterAt + 32) * sizeof(int32_t)));
+  ASZ_CUDA(cudaMalloc(&e->row_count, (size_t)8 << 20));
+  debug_pad(6);
   ASZ_CUDA(cudaMalloc(&e->actions, G * 8));
   ASZ_CUDA(cudaMalloc(&e->spawn_cells, G * sizeof(int32_t)));
   ASZ_CUDA(cudaMalloc(&e->ended, G));
   ASZ_CUDA(cudaMalloc(&e->rewards, G * 8));
+  debug_pad(10);
   ASZ_CUDA(cudaMalloc(&e->totals, 32 * sizeof(unsigned long long)));   // [0..15] totals, [16..23] profile build's cycle sums
   ASZ_CUDA(cudaMemset(e->totals, 0, 32 * sizeof(unsigned long long)));
   ASZ_CUDA(cudaMemset(e->ended, 0, G));
@@ -541,17 +571,73 @@ int asz_engine_destroy(asz_engine* e) {
   return ASZ_OK;
 }
 
-int asz_reset(asz_engine* e, void* stream) {
-  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
-  DeviceGuard guard(e->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  e->l2_dirty = true;      // bulk initialisation (and usually the caller's allocation of the batch buffer) leaves the L2 dirty
+static int reset_games(asz_engine* e, cudaStream_t st) {
   ASZ_CUDA(cudaMemsetAsync(e->totals, 0, 32 * sizeof(unsigned long long), st));
   switch (e->cfg.side) {
     case 7: return EnvLaunch<7>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
     case 11: return EnvLaunch<11>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
     default: return EnvLaunch<19>::reset(e->root, e->cfg.snakes, e->cfg.seed, st);
   }
+}
+
+// Picks the address of the kernel's hot word for THIS process (engines whose batch streams through the L2 only): for each
+// candidate, one L2 sweep and a few real tic + encode launches on the freshly initialised games into the engine's own plane
+// buffer, timed with events; the first candidate that shows the fast regime wins (about every second one does), otherwise the
+// best.  The caller re-initialises the games afterwards.  ~3 ms per candidate, once per asz_reset.
+static int select_hot_word(asz_engine* e, cudaStream_t st) {
+  asz_engine::L2Monitor& mon = e->l2mon;
+  const int saved = e->auto_condition;
+  asz_step_args a;
+  memset(&a, 0, sizeof a);
+  a.flags = ASZ_STEP_TIC | ASZ_STEP_ENCODE | ASZ_STEP_AUTO_RESET | ASZ_STEP_RANDOM_ACT; a.spawn_mode = ASZ_SPAWN_NATIVE;
+  a.d_planes = e->planes; a.d_row_ids = e->row_ids; a.max_rows = e->cfg.games * e->cfg.snakes; a.plane_pitch = e->pitch;
+  double best = 0.0;
+  int best_k = mon.candidate, rc = ASZ_OK;
+  for (int trial = 0; trial < 12 && rc == ASZ_OK; ++trial) {
+    const int k = mon.candidate + trial;
+    e->sched_off = hot_word_offset(k);
+    a.d_row_count = e->rows_ptr();
+    e->auto_condition = saved;                      // asz_condition_l2 is a no-op when conditioning is off
+    rc = asz_condition_l2(e, st);
+    e->auto_condition = 0;                          // no monitor inside the probe launches
+    for (int i = 0; i < 3 && rc == ASZ_OK; ++i) rc = asz_env_step(e, &a, st);
+    if (rc != ASZ_OK) break;
+    cudaEventRecord(mon.ev0, st);
+    for (int i = 0; i < 6 && rc == ASZ_OK; ++i) rc = asz_env_step(e, &a, st);
+    cudaMemcpyAsync(mon.h_rows, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(mon.ev1, st);
+    if (cudaEventSynchronize(mon.ev1) != cudaSuccess) { rc = ASZ_ERR_CUDA; break; }
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, mon.ev0, mon.ev1);
+    const double gbs = ms > 0.0f ? (double)*mon.h_rows * e->pitch * sizeof(float) * 6.0 / (ms * 1e-3) / 1e9 : 0.0;
+    if (gbs > best) { best = gbs; best_k = k; }
+    if (gbs >= e->l2_slow_gbs * 1.06) break;        // clearly the fast regime
+  }
+  e->auto_condition = saved;
+  const bool ended_on_best = hot_word_offset(best_k) == e->sched_off;
+  mon.candidate = best_k;
+  e->sched_off = hot_word_offset(best_k);
+  mon.last_gbs = best; mon.fails = 0; mon.pending = false; mon.since_sample = 0; mon.cooldown = 0;
+  // the probe's last launches ran in the fast regime on the chosen word: the L2 is conditioned already (re-initialising the games
+  // writes 23 MB, which does not disturb it); otherwise the first tic + encode launch starts with a sweep
+  e->l2_dirty = !(ended_on_best && best >= e->l2_slow_gbs * 1.06);
+  return rc;
+}
+
+int asz_reset(asz_engine* e, void* stream) {
+  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = reset_games(e, st);
+  if (rc != ASZ_OK) return rc;
+  if (streams_through_l2(e) && !e->hot_word_selected) {
+    rc = select_hot_word(e, st);
+    if (rc != ASZ_OK) return rc;
+    e->hot_word_selected = true;
+    return reset_games(e, st);                      // the probe stepped the games: start them again
+  }
+  e->l2_dirty = true;      // bulk initialisation usually leaves the L2 dirty
+  return ASZ_OK;
 }
 
 int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
@@ -582,13 +668,12 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.pitched = (a->plane_pitch == e->pitch && e->pitch != e->plane) ? 1 : 0;
   // rows are always counted in the engine's own counter (its L2 slice is known not to be the work counter's; a caller's
   // 4-byte buffer could land anywhere) and copied to the caller's d_row_count after the launch
-  p.row_count = e->row_count;
+  p.row_count = e->rows_ptr();
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals; p.prof = e->totals + 16;
-  p.sched = reinterpret_cast<unsigned long long*>(e->row_count);   // low word = e->row_count[0]: the row count the callers read
+  p.sched = reinterpret_cast<unsigned long long*>(e->rows_ptr());   // low word = the row count the callers read
   p.hints = e->step_hints;
   // "L2 conditioning": streaming launches (tic + encode into pitched rows of an engine whose batch is much larger than the L2)
-  const bool streaming = (a->flags & ASZ_STEP_TIC) && (a->flags & ASZ_STEP_ENCODE) && p.pitched && e->auto_condition &&
-                         (size_t)e->cfg.games * e->cfg.snakes * e->pitch * sizeof(float) >= ((size_t)192 << 20);
+  const bool streaming = (a->flags & ASZ_STEP_TIC) && (a->flags & ASZ_STEP_ENCODE) && p.pitched && streams_through_l2(e);
   asz_engine::L2Monitor& mon = e->l2mon;
   bool sample = false;
   if (streaming) {
@@ -600,7 +685,8 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
         if (bytes >= (double)((size_t)192 << 20)) {
           mon.last_gbs = bytes / (ms * 1e-3) / 1e9;
           mon.samples += 1;
-          if (mon.last_gbs < e->l2_slow_gbs) { mon.slow_samples += 1; mon.fails += 1; e->l2_dirty = true; }
+          // launches of asz_env_step_host also post their per-game results to pinned host memory: a lower bar for them
+          if (mon.last_gbs < e->l2_slow_gbs * (mon.pending_host ? 0.9 : 1.0)) { mon.slow_samples += 1; mon.fails += 1; e->l2_dirty = true; }
           else mon.fails = 0;
         }
       }
@@ -608,19 +694,27 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
     cudaGetLastError();                                                 // cudaErrorNotReady of the query is not an error
     if (mon.cooldown > 0) mon.cooldown -= 1;
     if (e->l2_dirty && mon.cooldown == 0) {
-      if (mon.fails >= 4) { mon.cooldown = 4096; mon.fails = 0; e->l2_dirty = false; }   // sweeps do not take here: stop trying for a while
+      if (mon.fails >= 2 && mon.rotations < 24) {
+        // two sweeps in a row did not help: the hot word sits in an L2 slice from which the fast regime cannot be reached.  Move
+        // it to the next candidate address (other address bits 7..22 => another slice); about every second candidate is good.
+        mon.candidate += 1; mon.rotations += 1; mon.fails = 0;
+        e->sched_off = hot_word_offset(mon.candidate);
+        p.sched = reinterpret_cast<unsigned long long*>(e->rows_ptr());
+        p.row_count = e->rows_ptr();
+      }
+      if (mon.fails >= 4) { mon.cooldown = 4096; mon.fails = 0; e->l2_dirty = false; }   // nothing helps here: stop trying for a while
       else {
         const int rc0 = asz_condition_l2(e, stream);
         if (rc0 != ASZ_OK) return rc0;
         mon.sweeps += 1;
-        mon.since_sample = 12;                                          // look at the result soon
+        mon.since_sample = 5;                                           // look at the result soon
       }
     }
-    if (!mon.pending && ++mon.since_sample >= 16) { sample = true; mon.since_sample = 0; }
+    if (!mon.pending && ++mon.since_sample >= 8) { sample = true; mon.since_sample = 0; mon.pending_host = e->host_step; }
   }
   if ((a->flags & ASZ_STEP_ENCODE) && !(a->flags & ASZ_STEP_TIC)) e->l2_dirty = true;   // encode-only launches out-run the HBM drain
   if (sample) ASZ_CUDA(cudaEventRecord(mon.ev0, st));
-  ASZ_CUDA(cudaMemsetAsync(e->row_count, 0, (kWorkCounterAt + 32) * sizeof(int32_t), st));
+  ASZ_CUDA(cudaMemsetAsync(p.sched, 0, sizeof(unsigned long long), st));
   int rc;
   switch (e->cfg.side) {
     case 7: rc = EnvLaunch<7>::step(p, st); break;
@@ -629,12 +723,12 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   }
   if (rc != ASZ_OK) return rc;
   if (sample) {
-    ASZ_CUDA(cudaMemcpyAsync(mon.h_rows, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ASZ_CUDA(cudaMemcpyAsync(mon.h_rows, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     ASZ_CUDA(cudaEventRecord(mon.ev1, st));
     mon.pending = true;
   }
-  if (a->d_row_count && a->d_row_count != e->row_count)
-    ASZ_CUDA(cudaMemcpyAsync(a->d_row_count, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (a->d_row_count && a->d_row_count != e->rows_ptr())
+    ASZ_CUDA(cudaMemcpyAsync(a->d_row_count, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return ASZ_OK;
 }
 
@@ -658,7 +752,7 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
   memset(&a, 0, sizeof a);
   a.flags = flags; a.spawn_mode = spawn_mode; a.d_actions = e->actions; a.d_spawn_cells = e->spawn_cells;
   a.d_planes = e->planes; a.d_row_ids = e->row_ids; a.max_rows = (int32_t)(G * (size_t)e->cfg.snakes); a.plane_pitch = e->pitch;
-  a.d_row_count = e->row_count; a.d_ended = e->ended; a.d_rewards = e->rewards;
+  a.d_row_count = e->rows_ptr(); a.d_ended = e->ended; a.d_rewards = e->rewards;
   // Result buffers in pinned (page-locked, UVA-mapped) host memory are written by the kernel itself, one posted PCIe write
   // per game while the launch runs, instead of by two device->host copies after it (ASZ_HOST_ZEROCOPY=0 disables).
   static int zero_copy = -1;
@@ -675,13 +769,15 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
     cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers: not ours
   }
   e->step_hints = e->host_hints;
+  e->host_step = true;
   int rc = asz_env_step(e, &a, stream);
+  e->host_step = false;
   e->step_hints = e->device_hints;
   if (rc != ASZ_OK) return rc;
   if (h_ended && !zc_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, e->ended, G, cudaMemcpyDeviceToHost, st));
   if (h_rewards && !zc_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, e->rewards, G * 8, cudaMemcpyDeviceToHost, st));
   int32_t rows = 0;
-  ASZ_CUDA(cudaMemcpyAsync(&rows, e->row_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  ASZ_CUDA(cudaMemcpyAsync(&rows, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   ASZ_CUDA(cudaStreamSynchronize(st));
   if (h_row_count) *h_row_count = rows;
   if ((h_planes || h_row_ids) && rows > 0) {
@@ -714,7 +810,7 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
   ASZ_CUDA(cudaDeviceSynchronize());
   ASZ_CUDA(cudaMemcpy(h_totals, e->totals, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   h_totals[9] = e->l2mon.sweeps; h_totals[10] = e->l2mon.samples; h_totals[11] = e->l2mon.slow_samples;   // host-side: L2 monitor
-  h_totals[12] = (uint64_t)e->l2mon.last_gbs;
+  h_totals[12] = (uint64_t)e->l2mon.last_gbs; h_totals[13] = e->l2mon.rotations;
   return ASZ_OK;
 }
 

@@ -143,18 +143,18 @@ int asz_records_append(asz_engine* e, const float* d_root_q, int64_t* h_count, v
   a.flags = ASZ_STEP_ENCODE; a.spawn_mode = ASZ_SPAWN_NONE;
   a.d_planes = r->planes; a.d_row_ids = r->ids; a.max_rows = (int32_t)r->capacity; a.row_base = (int32_t)r->count;
   a.plane_pitch = e->pitch;
-  a.d_row_count = e->row_count;
+  a.d_row_count = e->rows_ptr();
   rc = asz_env_step(e, &a, stream);
   if (rc != ASZ_OK) return rc;
   const int64_t room = r->capacity - r->count;
   const int64_t max_new = std::min<int64_t>(room, (int64_t)e->cfg.games * e->cfg.snakes);
   if (max_new > 0) {
-    records_values_kernel<<<(unsigned)((max_new + 255) / 256), 256, 0, st>>>(q, r->ids, e->row_count, r->count, r->capacity, r->n_appends,
+    records_values_kernel<<<(unsigned)((max_new + 255) / 256), 256, 0, st>>>(q, r->ids, e->rows_ptr(), r->count, r->capacity, r->n_appends,
                                                                             r->values, r->turns);
     if (!cuda_ok(cudaGetLastError(), "records_values_kernel")) return ASZ_ERR_CUDA;
   }
   int32_t rows = 0;
-  ASZ_CUDA(cudaMemcpyAsync(&rows, e->row_count, sizeof rows, cudaMemcpyDeviceToHost, st));
+  ASZ_CUDA(cudaMemcpyAsync(&rows, e->rows_ptr(), sizeof rows, cudaMemcpyDeviceToHost, st));
   ASZ_CUDA(cudaStreamSynchronize(st));
   r->n_appends += 1;
   if ((int64_t)rows > room) {

@@ -71,7 +71,8 @@ class Engine:
         up to 8 floats: every plane starts on a 32-byte sector, the fast path of the encode kernel), so this is a strided
         view; `.contiguous()` / indexing give dense copies."""
         if self._planes is None:
-            self._planes_flat = torch.zeros(self.max_rows * self.pitch + 8, dtype=torch.float32, device=self.device)
+            # empty, not zeros: a 1.4 GB fill would leave the L2 full of dirty lines right before the first launch (DESIGN.md 4.1)
+            self._planes_flat = torch.empty(self.max_rows * self.pitch + 8, dtype=torch.float32, device=self.device)
             self._planes = torch.as_strided(self._planes_flat, (self.max_rows, self.N, self.N, 3), (self.pitch, 3 * self.N, 3, 1))
         return self._planes
 
@@ -142,7 +143,7 @@ class Engine:
         t = np.zeros(16, np.uint64)
         check(self.L.asz_get_totals(self.h, _np(t)))
         return dict(zip(("wall", "body", "head", "starve", "food_eaten", "game_length", "episodes", "tics", "planes",
-                         "l2_sweeps", "l2_samples", "l2_slow_samples", "l2_last_gbs"), t.tolist()))
+                         "l2_sweeps", "l2_samples", "l2_slow_samples", "l2_last_gbs", "l2_rotations"), t.tolist()))
 
     # ---- convenience used by tests and the drop-in classes -------------------------------------------------------
     def rows(self):

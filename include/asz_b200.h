@@ -137,7 +137,7 @@ int asz_condition_l2(asz_engine* e, void* stream);
 /* Running totals over games that ended since the last asz_reset (mp_game_runner.py:56-61, 71-76 divides by G):
  * h_totals[16] = wall, body, head, starve, food_eaten, game_length, episodes_finished, tics_executed, planes_written,
  * then the L2 monitor of asz_env_step (conditioning sweeps run, launches sampled, samples found in the slow regime, GB/s of
- * the last sample), then 3 reserved slots.  Synchronous. */
+ * the last sample, times the kernel's hot scheduling word was moved to another address), then 2 reserved slots.  Synchronous. */
 int asz_get_totals(asz_engine* e, uint64_t* h_totals);
 
 /* device pointers of the packed root-game records, read-only for callers: d_ptrs[0] = cells (u16 [G][padded cells]),
