@@ -49,6 +49,9 @@ SYMBOLS = [
     ("asz_set_state", C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     ("asz_env_step", C.c_int, [_vp, C.POINTER(StepArgs), _vp]),
     ("asz_env_step_host", C.c_int, [_vp, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("asz_env_submit_host", C.c_int, [_vp, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("asz_env_wait_host", C.c_int, [_vp, _i32, _vp]),
+    ("asz_internal_set_hot_word", C.c_int, [_vp, _i32]),
     ("asz_condition_l2", C.c_int, [_vp, _vp]),
     ("asz_get_totals", C.c_int, [_vp, _vp]),
     ("asz_internal_profile", C.c_int, [_vp, _vp]),

@@ -100,6 +100,18 @@ struct asz_engine {
     int candidate = 0;
     double last_gbs = 0.0;
   } l2mon;
+  // asz_env_submit_host / asz_env_wait_host: two steps in flight, the inputs of the next one copied under the kernel of this one
+  struct HostPipe {
+    bool ready = false;
+    cudaStream_t copy = nullptr;                 // host -> device copies of the steps' inputs
+    cudaEvent_t copied[2] = {nullptr, nullptr};  // slot's inputs are on the device
+    cudaEvent_t done[2] = {nullptr, nullptr};    // slot's launch and result copies have finished
+    uint8_t* actions[2] = {nullptr, nullptr};    // [G*8] per slot
+    int32_t* spawn[2] = {nullptr, nullptr};      // [G] per slot
+    int32_t* h_rows = nullptr;                   // pinned, one 64-byte line per slot
+    bool busy[2] = {false, false};
+    int next = 0;
+  } hostpipe;
   double l2_slow_gbs = 5500.0;     // ASZ_L2_SLOW_GBS: between the two regimes of a B200 (about 4,400 and 6,600 GB/s of plane bytes)
   asz::SearchState* search = nullptr;
   asz::RecordStore* records = nullptr;   // device-resident training records (asz_records_*)
@@ -111,4 +123,5 @@ void gameset_free(GameSet& gs);
 int search_create(asz_engine* e);
 void search_destroy(asz_engine* e);
 void records_destroy(asz_engine* e);
+void host_pipe_destroy(asz_engine* e);
 }  // namespace asz

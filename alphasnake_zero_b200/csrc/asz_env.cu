@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
                    : "memory");
     }
   };
+#if defined(ASZ_EXP_HALF_ATOM)
+  int exp_spare = 0, exp_row = 0, exp_nxt = 0;
+#endif
   if (g < p.G) { prefetch(g); act_slot ^= 1; }
   while (g < p.G) {
     ASZ_PROF_DECL
@@ -239,8 +242,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         n_rows = __popc(live_mask);
       }
       if (lane == 0) {
+#if defined(ASZ_EXP_HALF_ATOM)      // timing experiment only (rows are NOT compact): one atomic per ASZ_EXP_HALF_ATOM games
+        if (exp_spare > 0) { row = exp_row; nxt = exp_nxt; exp_row += 4; exp_nxt += 1; exp_spare -= 1; }
+        else {
+          constexpr int NB = ASZ_EXP_HALF_ATOM;
+          const unsigned long long t = atomicAdd(p.sched, ((unsigned long long)NB << 32) | (unsigned long long)(unsigned)(n_rows + 4 * (NB - 1)));
+          row = (int)(uint32_t)t; nxt = n_warps + (int)(t >> 32);
+          exp_row = row + n_rows; exp_nxt = nxt + 1; exp_spare = NB - 1;
+        }
+#elif defined(ASZ_EXP_ATOM_HINT)    // experiment: the hot line carries the evict_last policy
+        unsigned long long t;
+        asm volatile("atom.global.add.L2::cache_hint.u64 %0, [%1], %2, %3;" : "=l"(t) : "l"(p.sched), "l"((1ull << 32) | (unsigned long long)(unsigned)n_rows), "l"(l2_policy_evict_last()) : "memory");
+        row = (int)(uint32_t)t; nxt = n_warps + (int)(t >> 32);
+#else
         const unsigned long long t = atomicAdd(p.sched, (1ull << 32) | (unsigned long long)(unsigned)n_rows);
         row = (int)(uint32_t)t; nxt = n_warps + (int)(t >> 32);
+#if defined(ASZ_EXP_DOUBLE_ATOM)    // timing experiment: a second returning atomic on the same word per game
+        row += (int)(atomicAdd(p.sched, 0ull) >> 63);
+#endif
+#endif
         s_wtot[warp][8] += (uint32_t)n_rows;
       }
       // write the record back
@@ -561,6 +581,7 @@ int asz_engine_destroy(asz_engine* e) {
   DeviceGuard guard(e->device);
   search_destroy(e);
   records_destroy(e);
+  host_pipe_destroy(e);
   gameset_free(e->root);
   if (e->l2mon.ev0) cudaEventDestroy(e->l2mon.ev0);
   if (e->l2mon.ev1) cudaEventDestroy(e->l2mon.ev1);
@@ -732,25 +753,79 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   return ASZ_OK;
 }
 
-int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
-                      const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, int32_t* h_row_count,
-                      float* h_planes, int32_t* h_row_ids, void* stream) {
-  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+// ---- host-buffer path: submit / wait, two steps in flight ------------------------------------------------------------------------
+// The step's inputs go host -> device on the engine's own copy stream, so that the copy of step k+1 runs under the kernel of
+// step k; the kernel waits for its copy through an event.  The per-game results are written by the kernel itself into the
+// caller's pinned buffers (posted PCIe writes while the launch runs); the row count follows as one 4-byte copy into a pinned word
+// of the slot, then the slot's event.  asz_env_wait_host blocks on that event only.
+static int host_pipe_create(asz_engine* e) {
+  asz_engine::HostPipe& hp = e->hostpipe;
+  if (hp.ready) return ASZ_OK;
+  const size_t G = (size_t)e->cfg.games;
+  ASZ_CUDA(cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking));
+  ASZ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hp.h_rows), 2 * 16 * sizeof(int32_t), cudaHostAllocDefault));
+  for (int i = 0; i < 2; ++i) {
+    ASZ_CUDA(cudaEventCreateWithFlags(&hp.copied[i], cudaEventDisableTiming));
+    ASZ_CUDA(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
+    ASZ_CUDA(cudaMalloc(&hp.actions[i], G * 8));
+    ASZ_CUDA(cudaMalloc(&hp.spawn[i], G * sizeof(int32_t)));
+  }
+  hp.ready = true;
+  return ASZ_OK;
+}
+
+}  // extern "C"
+namespace asz {
+void host_pipe_destroy(asz_engine* e) {
+  asz_engine::HostPipe& hp = e->hostpipe;
+  for (int i = 0; i < 2; ++i) {
+    if (hp.copied[i]) cudaEventDestroy(hp.copied[i]);
+    if (hp.done[i]) cudaEventDestroy(hp.done[i]);
+    cudaFree(hp.actions[i]); cudaFree(hp.spawn[i]);
+  }
+  if (hp.h_rows) cudaFreeHost(hp.h_rows);
+  if (hp.copy) cudaStreamDestroy(hp.copy);
+  hp = asz_engine::HostPipe();
+}
+}  // namespace asz
+extern "C" {
+
+// device-visible alias of a pinned host buffer (nullptr for pageable memory).  Asked every step on purpose: an address may be
+// unpinned and reused between two steps.
+static void* pinned_alias(void* h) {
+  if (!h) return nullptr;
+  cudaPointerAttributes at;
+  void* d = nullptr;
+  if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) d = at.devicePointer;
+  cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers: not ours
+  return d;
+}
+
+int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
+                        const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, void* stream, int32_t* ticket) {
+  if (!e || !ticket) { set_error("null argument"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
-  NvtxRange nvtx("asz:env_step_host");
+  NvtxRange nvtx("asz:env_submit_host");
+  { const int rc0 = host_pipe_create(e); if (rc0 != ASZ_OK) return rc0; }
+  asz_engine::HostPipe& hp = e->hostpipe;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t G = (size_t)e->cfg.games;
-  if ((flags & ASZ_STEP_TIC) && !(flags & ASZ_STEP_RANDOM_ACT)) {
-    if (!h_actions) { set_error("h_actions is null"); return ASZ_ERR_ARG; }
-    ASZ_CUDA(cudaMemcpyAsync(e->actions, h_actions, G * 8, cudaMemcpyHostToDevice, st));
-  }
-  if ((flags & ASZ_STEP_TIC) && spawn_mode == ASZ_SPAWN_REPLAY) {
-    if (!h_spawn_cells) { set_error("h_spawn_cells is null"); return ASZ_ERR_ARG; }
-    ASZ_CUDA(cudaMemcpyAsync(e->spawn_cells, h_spawn_cells, G * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const int slot = hp.next;
+  if (hp.busy[slot]) { set_error("asz_env_submit_host: two steps are in flight already; asz_env_wait_host the oldest first"); return ASZ_ERR_ARG; }
+  const bool need_actions = (flags & ASZ_STEP_TIC) && !(flags & ASZ_STEP_RANDOM_ACT);
+  const bool need_spawn = (flags & ASZ_STEP_TIC) && spawn_mode == ASZ_SPAWN_REPLAY;
+  if (need_actions && !h_actions) { set_error("h_actions is null"); return ASZ_ERR_ARG; }
+  if (need_spawn && !h_spawn_cells) { set_error("h_spawn_cells is null"); return ASZ_ERR_ARG; }
+  if (need_actions || need_spawn) {
+    // the slot's device buffers were last read by the step waited for two submissions ago: free to overwrite
+    if (need_actions) ASZ_CUDA(cudaMemcpyAsync(hp.actions[slot], h_actions, G * 8, cudaMemcpyHostToDevice, hp.copy));
+    if (need_spawn) ASZ_CUDA(cudaMemcpyAsync(hp.spawn[slot], h_spawn_cells, G * sizeof(int32_t), cudaMemcpyHostToDevice, hp.copy));
+    ASZ_CUDA(cudaEventRecord(hp.copied[slot], hp.copy));
+    ASZ_CUDA(cudaStreamWaitEvent(st, hp.copied[slot], 0));
   }
   asz_step_args a;
   memset(&a, 0, sizeof a);
-  a.flags = flags; a.spawn_mode = spawn_mode; a.d_actions = e->actions; a.d_spawn_cells = e->spawn_cells;
+  a.flags = flags; a.spawn_mode = spawn_mode; a.d_actions = hp.actions[slot]; a.d_spawn_cells = hp.spawn[slot];
   a.d_planes = e->planes; a.d_row_ids = e->row_ids; a.max_rows = (int32_t)(G * (size_t)e->cfg.snakes); a.plane_pitch = e->pitch;
   a.d_row_count = e->rows_ptr(); a.d_ended = e->ended; a.d_rewards = e->rewards;
   // Result buffers in pinned (page-locked, UVA-mapped) host memory are written by the kernel itself, one posted PCIe write
@@ -759,26 +834,48 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
   if (zero_copy < 0) { const char* v = getenv("ASZ_HOST_ZEROCOPY"); zero_copy = v ? atoi(v) : 1; }
   bool zc_ended = false, zc_rewards = false;
   if (zero_copy && (flags & ASZ_STEP_TIC)) {
-    cudaPointerAttributes at;
-    if (h_ended && cudaPointerGetAttributes(&at, h_ended) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-      a.d_ended = static_cast<uint8_t*>(at.devicePointer); zc_ended = true;
-    }
-    if (h_rewards && cudaPointerGetAttributes(&at, h_rewards) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-      a.d_rewards = static_cast<int8_t*>(at.devicePointer); zc_rewards = true;
-    }
-    cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers: not ours
+    if (void* d = pinned_alias(h_ended)) { a.d_ended = static_cast<uint8_t*>(d); zc_ended = true; }
+    if (void* d = pinned_alias(h_rewards)) { a.d_rewards = static_cast<int8_t*>(d); zc_rewards = true; }
   }
   e->step_hints = e->host_hints;
   e->host_step = true;
-  int rc = asz_env_step(e, &a, stream);
+  const int rc = asz_env_step(e, &a, stream);
   e->host_step = false;
   e->step_hints = e->device_hints;
   if (rc != ASZ_OK) return rc;
   if (h_ended && !zc_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, e->ended, G, cudaMemcpyDeviceToHost, st));
   if (h_rewards && !zc_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, e->rewards, G * 8, cudaMemcpyDeviceToHost, st));
-  int32_t rows = 0;
-  ASZ_CUDA(cudaMemcpyAsync(&rows, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  ASZ_CUDA(cudaStreamSynchronize(st));
+  ASZ_CUDA(cudaMemcpyAsync(hp.h_rows + 16 * slot, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  ASZ_CUDA(cudaEventRecord(hp.done[slot], st));
+  hp.busy[slot] = true;
+  hp.next = slot ^ 1;
+  *ticket = slot;
+  return ASZ_OK;
+}
+
+int asz_env_wait_host(asz_engine* e, int32_t ticket, int32_t* h_row_count) {
+  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  asz_engine::HostPipe& hp = e->hostpipe;
+  if (ticket < 0 || ticket > 1 || !hp.ready || !hp.busy[ticket]) { set_error("asz_env_wait_host: no step in flight under this ticket"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
+  hp.busy[ticket] = false;
+  ASZ_CUDA(cudaEventSynchronize(hp.done[ticket]));
+  if (h_row_count) *h_row_count = hp.h_rows[16 * ticket];
+  return ASZ_OK;
+}
+
+int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
+                      const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, int32_t* h_row_count,
+                      float* h_planes, int32_t* h_row_ids, void* stream) {
+  if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
+  NvtxRange nvtx("asz:env_step_host");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t ticket = -1, rows = 0;
+  int rc = asz_env_submit_host(e, flags, spawn_mode, h_actions, h_spawn_cells, h_ended, h_rewards, stream, &ticket);
+  if (rc != ASZ_OK) return rc;
+  rc = asz_env_wait_host(e, ticket, &rows);
+  if (rc != ASZ_OK) return rc;
   if (h_row_count) *h_row_count = rows;
   if ((h_planes || h_row_ids) && rows > 0) {
     // the engine's buffer is pitched, the caller's rows are dense: one strided copy
@@ -823,6 +920,16 @@ int asz_internal_profile(asz_engine* e, uint64_t* h_cycles) {
   return ASZ_OK;
 }
 
+// experiments (tools/env_hot.py): put the kernel's hot word at candidate address k and keep it there
+int asz_internal_set_hot_word(asz_engine* e, int32_t k) {
+  if (!e || k < 0) { set_error("bad argument"); return ASZ_ERR_ARG; }
+  DeviceGuard guard(e->device);
+  ASZ_CUDA(cudaDeviceSynchronize());
+  e->l2mon.candidate = k;
+  e->sched_off = hot_word_offset(k);
+  e->hot_word_selected = true;
+  return ASZ_OK;
+}
 int asz_internal_state(asz_engine* e, void** d_ptrs) {
   if (!e || !d_ptrs) { set_error("null argument"); return ASZ_ERR_ARG; }
   d_ptrs[0] = e->root.cells; d_ptrs[1] = e->root.snakes; d_ptrs[2] = e->root.meta;

@@ -134,6 +134,23 @@ class Engine:
         a.d_rewards = self.rewards.data_ptr()
         check(self.L.asz_env_step(self.h, C.byref(a), self.stream))
 
+    def submit_host(self, h_actions, h_ended, h_rewards, spawn_mode=SPAWN_NATIVE, tic=True, encode=True, auto_reset=False,
+                    random_actions=False, h_spawn_cells=None):
+        """asz_env_submit_host: one step with HOST buffers (pinned torch tensors or None), enqueued without waiting.  Returns the
+        ticket for wait_host; two steps may be in flight (the inputs of the second are copied under the kernel of the first)."""
+        flags = (STEP_TIC if tic else 0) | (STEP_ENCODE if encode else 0) | (STEP_AUTO_RESET if auto_reset else 0) | \
+                (STEP_RANDOM_ACT if random_actions else 0)
+        ticket = C.c_int32(-1)
+        check(self.L.asz_env_submit_host(self.h, flags, spawn_mode, _ptr(h_actions), _ptr(h_spawn_cells), _ptr(h_ended),
+                                         _ptr(h_rewards), self.stream, C.byref(ticket)))
+        return ticket.value
+
+    def wait_host(self, ticket):
+        """asz_env_wait_host: blocks until the step's host results are complete; returns the number of plane rows it wrote."""
+        rows = C.c_int32(0)
+        check(self.L.asz_env_wait_host(self.h, ticket, C.byref(rows)))
+        return rows.value
+
     def condition_l2(self):
         """one read sweep that leaves the L2 full of clean lines: the fast regime of the fused tic + encode kernel on engines whose
         batch is much larger than the L2 (asz_condition_l2; a no-op for small engines)"""

@@ -479,19 +479,42 @@ def run_ours(args, rank, world, local_rank):
         _lib.check(L.asz_env_step_host(eng.h, flags, _lib.SPAWN_NATIVE, C.c_void_p(act_pool[i % n_pool].data_ptr()), None,
                                        C.c_void_p(h_ended.data_ptr()), C.c_void_p(h_rewards.data_ptr()), C.byref(rows),
                                        None, None, eng.stream))
-    for i in range(W):
-        e2e_step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_b = eng.totals()
-    barrier()
-    e0.record()
-    for i in range(K):
-        e2e_step(i)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_steps_local = eng.totals()["tics"] - t_b["tics"]
+
+    def timed_e2e(run_steps):
+        for i in range(W):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_b = eng.totals()
+        barrier()
+        e0.record()
+        run_steps()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), eng.totals()["tics"] - t_b["tics"]
+
+    # (a) one synchronous call per step: copy in, launch, results out, wait -- nothing of step k+1 starts before step k is back
+    def sync_steps():
+        for i in range(K):
+            e2e_step(i)
+    e2e_sync_ms, e2e_sync_steps_local = timed_e2e(sync_steps)
+
+    # (b) the same steps as submit / wait with two steps in flight (the uniform-random moves of configs[1] do not depend on the
+    # previous step's result): every step still brings its own actions from pinned host memory and lands its own ended / rewards /
+    # row count in host memory inside the timed region, but the copy of step k+1 runs under the kernel of step k.
+    h_ended2 = [h_ended, torch.zeros(GAMES, dtype=torch.uint8).pin_memory()]
+    h_rewards2 = [h_rewards, torch.zeros(GAMES, 8, dtype=torch.int8).pin_memory()]
+    kw_host = dict(spawn_mode=_lib.SPAWN_NATIVE, tic=True, encode=True, auto_reset=True)
+    e2e_rows = [0]
+
+    def piped_steps():
+        t_prev = eng.submit_host(act_pool[0], h_ended2[0], h_rewards2[0], **kw_host)
+        for i in range(1, K):
+            t_next = eng.submit_host(act_pool[i % n_pool], h_ended2[i & 1], h_rewards2[i & 1], **kw_host)
+            e2e_rows[0] += eng.wait_host(t_prev)
+            t_prev = t_next
+        e2e_rows[0] += eng.wait_host(t_prev)
+    e2e_ms, e2e_steps_local = timed_e2e(piped_steps)
 
     # what the headline e2e number does NOT do: ship the planes to the host.  The consumer of the planes is the value network on
     # the same GPU; a caller that wants them in host memory pays PCIe for ~1 GB per step (reported once, rank 0, 3 steps).
@@ -606,18 +629,21 @@ def run_ours(args, rank, world, local_rank):
             bcast = {"error": repr(ex)}
 
     # ---- reduce over ranks: max time, sum of work ----------------------------------------------------------------
-    vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local)], dtype=torch.float64, device=dev)
+    vals = torch.tensor([ms, e2e_ms, float(steps_local), float(planes_local), float(e2e_steps_local), e2e_sync_ms, float(e2e_sync_steps_local)],
+                        dtype=torch.float64, device=dev)
     rank_ms = None
     if world > 1:
         allv = [torch.zeros_like(vals) for _ in range(world)]
         dist.all_gather(allv, vals)
-        rank_ms = {"device_resident": [round(float(v[0]) / K, 5) for v in allv], "e2e": [round(float(v[1]) / K, 5) for v in allv]}
+        rank_ms = {"device_resident": [round(float(v[0]) / K, 5) for v in allv], "e2e": [round(float(v[1]) / K, 5) for v in allv],
+                   "e2e_synchronous": [round(float(v[5]) / K, 5) for v in allv]}
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, e2e_ms = float(mx[0]), float(mx[1])
-        steps_all, planes_all, e2e_steps_all = float(sm[2]), float(sm[3]), float(sm[4])
+        ms, e2e_ms, e2e_sync_ms = float(mx[0]), float(mx[1]), float(mx[5])
+        steps_all, planes_all, e2e_steps_all, e2e_sync_steps_all = float(sm[2]), float(sm[3]), float(sm[4]), float(sm[6])
     else:
         steps_all, planes_all, e2e_steps_all = float(steps_local), float(planes_local), float(e2e_steps_local)
+        e2e_sync_steps_all = float(e2e_sync_steps_local)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -652,7 +678,11 @@ def run_ours(args, rank, world, local_rank):
                      "note": "algorithmic bytes count 5,292 B per plane; the kernel writes 5,312 B (rows padded to 32-byte sectors)"},
         "e2e": {"value": e2e_steps_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": GAMES * 8,
                 "d2h_bytes_per_step": GAMES + GAMES * 8 + 4,
-                "note": "asz_env_step_host: pinned host actions in, per-game ended/rewards + row count out; planes stay in HBM for the network"},
+                "note": "asz_env_submit_host / asz_env_wait_host, two steps in flight: every step copies its pinned host actions in and "
+                        "lands its per-game ended/rewards + row count in host memory inside the timed region; the copy of step k+1 runs "
+                        "under the kernel of step k; planes stay in HBM for the network",
+                "synchronous": {"value": e2e_sync_steps_all / (e2e_sync_ms * 1e-3), "unit": UNIT,
+                                "note": "asz_env_step_host: one blocking call per step (copy in, launch, results out, wait)"}},
         "gpu_launches": K, "clocks": clocks, "launch_us": launch_us,
         "l2_monitor": {k: t_after[k] for k in ("l2_sweeps", "l2_samples", "l2_slow_samples", "l2_last_gbs", "l2_rotations")},
     }

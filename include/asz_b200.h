@@ -125,6 +125,19 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
                       const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, int32_t* h_row_count,
                       float* h_planes, int32_t* h_row_ids, void* stream);
 
+/* The same step as two calls, so that a caller can keep two steps in flight: asz_env_submit_host enqueues the copy of the
+ * step's inputs (on a copy stream of the engine: it runs under the previous step's kernel), the launch and the result
+ * transfers, and returns a ticket (0 or 1) without waiting; asz_env_wait_host blocks until that step's h_ended / h_rewards
+ * are complete in host memory and returns its row count.  At most two tickets are outstanding (a third submit is an
+ * error); steps execute in submission order on `stream`, and the planes of a step stay in the engine's buffer until the next
+ * step's launch, in stream order, overwrites them (enqueue their consumer on `stream` between the two submits).  The host
+ * buffers of a step must stay untouched until its wait returns (two steps in flight need two sets of result buffers).
+ * This is Game.tic for a batch of games whose next moves do not depend on this step's result at the time of the call:
+ * uniform-random play (BASELINE.json configs[1]), replayed traces, or two populations stepped alternately. */
+int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
+                        const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, void* stream, int32_t* ticket);
+int asz_env_wait_host(asz_engine* e, int32_t ticket, int32_t* h_row_count);
+
 /* Optional conditioning of the L2 before a long run of asz_env_step launches on a large engine (a batch much larger than the
  * L2): one read sweep of ~1.25 GB over the engine's plane buffer, which leaves the L2 full of clean lines.  The fused kernel
  * then runs in its fast regime (~150 us instead of ~220 us per 65,536-game launch) until something else streams writes
@@ -149,6 +162,8 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals);
  * the last call, h_cycles[8] = record wait, tic, write-back, work-counter wait + prefetch, cell view + row wait, encode,
  * staging-buffer wait (inside encode), unused; all zero in the product build.  Synchronous. */
 int asz_internal_profile(asz_engine* e, uint64_t* h_cycles);
+/* experiments only (tools/env_hot.py): pins the fused kernel's scheduling word to the k-th candidate address */
+int asz_internal_set_hot_word(asz_engine* e, int32_t k);
 int asz_internal_state(asz_engine* e, void** d_ptrs);
 /* device pointer of the engine's internal plane buffer (capacity G*S rows, asz_plane_pitch() floats apart) and row-id buffer */
 float* asz_internal_planes(asz_engine* e);

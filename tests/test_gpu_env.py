@@ -298,6 +298,56 @@ def test_native_run_against_oracle(side, S, dec, G, tics):
     eng.close()
 
 
+def test_env_submit_wait_host_pipeline_equals_synchronous_steps():
+    """asz_env_submit_host / asz_env_wait_host with two steps in flight: per-step host results, row counts and the final game
+    states equal those of the same steps through the synchronous asz_env_step_host; a third submit without a wait is an error."""
+    import ctypes as C
+    import torch
+    from alphasnake_zero_b200 import _lib
+    from alphasnake_zero_b200.engine import AszError
+    G, T = 512, 60
+    rng = np.random.default_rng(5)
+    acts = [torch.from_numpy(rng.integers(0, 3, size=(G, 8), dtype=np.uint8)).pin_memory() for _ in range(T)]
+    ea, eb = _engine(side=11, snakes=4, games=G, seed=11), _engine(side=11, snakes=4, games=G, seed=11)
+    ea.reset(); eb.reset()
+    L = _lib.lib()
+    flags = _lib.STEP_TIC | _lib.STEP_ENCODE | _lib.STEP_AUTO_RESET
+    # synchronous reference run
+    end_s = torch.zeros(G, dtype=torch.uint8).pin_memory(); rew_s = torch.zeros(G, 8, dtype=torch.int8).pin_memory()
+    rows = C.c_int32(0)
+    want = []
+    for t in range(T):
+        _lib.check(L.asz_env_step_host(ea.h, flags, 2, C.c_void_p(acts[t].data_ptr()), None, C.c_void_p(end_s.data_ptr()),
+                                       C.c_void_p(rew_s.data_ptr()), C.byref(rows), None, None, ea.stream))
+        want.append((end_s.numpy().copy(), rew_s.numpy().copy(), rows.value))
+    # pipelined run: submit t+1 before waiting for t
+    end_p = [torch.zeros(G, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    rew_p = [torch.zeros(G, 8, dtype=torch.int8).pin_memory() for _ in range(2)]
+    kw = dict(spawn_mode=2, tic=True, encode=True, auto_reset=True)
+    tickets = [eb.submit_host(acts[0], end_p[0], rew_p[0], **kw)]
+    seen_end = 0
+    for t in range(T):
+        if t + 1 < T:
+            tickets.append(eb.submit_host(acts[t + 1], end_p[(t + 1) & 1], rew_p[(t + 1) & 1], **kw))
+            if t == 0:
+                with pytest.raises(AszError):                       # two steps in flight already
+                    eb.submit_host(acts[2], end_p[0], rew_p[0], **kw)
+        n = eb.wait_host(tickets[t])
+        w_end, w_rew, w_rows = want[t]
+        assert n == w_rows, t
+        assert np.array_equal(end_p[t & 1].numpy(), w_end) and np.array_equal(rew_p[t & 1].numpy(), w_rew), t
+        seen_end += int(w_end.sum())
+    assert seen_end > 0
+    with pytest.raises(AszError):
+        eb.wait_host(tickets[-1])                                   # already waited for
+    torch.cuda.synchronize()
+    for gi in range(0, G, 17):
+        assert_dump_equal(eb.get_state(gi), ea.get_state(gi), "game %d" % gi)
+    ta, tb = ea.totals(), eb.totals()
+    assert all(ta[k] == tb[k] for k in ("tics", "planes", "episodes", "wall", "body", "head", "starve", "food_eaten"))
+    ea.close(); eb.close()
+
+
 def test_env_step_host_roundtrip():
     """asz_env_step_host: host buffers in, host results out (the e2e path of bench.py)."""
     import ctypes as C
