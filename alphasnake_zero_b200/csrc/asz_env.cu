@@ -1,16 +1,17 @@
 // asz_env.cu -- lockstep Battlesnake tic with the plane encoding fused in, plus the env part of the C ABI.
 //
-// Kernel (env_step_kernel): persistent, 3 CTAs x 8 warps per SM, one warp = one game at a time.  A warp loads its game record
-// (cells + snakes + meta, ~350 B at 11x11x4; prefetched one game ahead), steps it in shared memory (asz_game.cuh: warp_tic),
-// writes the record back, takes its rows of the batch AND its next game with ONE 64-bit atomicAdd, and encodes the plane of
-// every surviving snake (5,292 B each at 11x11) into the network's input batch: the cells are scattered into a staged window
-// in shared memory and the copy engine (cp.async.bulk shared -> global) writes the plane, wall runs from a constant buffer.
+// Kernel (env_step_kernel): persistent, 3 CTAs x 8 warps per SM, one warp = one game at a time, two games per scheduling ticket.
+// A warp loads a game record (cells + snakes + meta, ~350 B at 11x11x4; prefetched one game ahead), steps it in shared memory
+// (asz_game.cuh: warp_tic) and writes the record back -- for both games of its ticket -- then takes the ticket's rows of the
+// batch AND its next ticket with ONE 64-bit atomicAdd, and encodes the plane of every surviving snake (5,292 B each at 11x11)
+// into the network's input batch: the cells are scattered into a staged window in shared memory and the copy engine
+// (cp.async.bulk shared -> global) writes the plane, wall runs from a constant buffer.
 //   pitched rows (the engine's own buffers, asz_plane_pitch): planes start on 32-byte sectors, a game's planes are one
 //     sequence of bulk copies (warp_encode_game_v3b), no per-plane edge handling;
 //   dense rows (a caller's [rows][N][N][3] tensor): warp_encode_v2, three copies per plane + edge floats by single lanes.
-// Roofline: HBM write bandwidth (planes are > 95 % of the bytes).  The kernel has two timing regimes that
-// depend on the state of the L2 and on where its one hot word lives; "L2 conditioning" below and the monitor in asz_env_step
-// keep it in the fast one.
+// Roofline: HBM write bandwidth (planes are > 95 % of the bytes).  What the kernel must NOT be bound by is the
+// rate at which one L2 slice serves atomics on one address (2.3 - 3.6 ns each): with one atomic per game that was the
+// bound, and the two values were the "two timing regimes" of rounds 1 and 2.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +49,7 @@ struct EnvParams {
   int device, n_sm;    // the engine's device and its multiprocessor count (grid size of the persistent kernel)
   int pitched;         // 1: plane rows are PitchGeo::PITCH floats apart (32-byte aligned rows), 0: dense rows of PLANE floats
   int row_base;        // rows of this launch are written at [row_base, row_base + n) of planes / row_ids / keys (max_rows is absolute)
+  int pair_tickets, n_tickets;   // scheduling tickets of the launch (set by EnvLaunch::launch): the first pair_tickets are two games each
 };
 
 // Phase timers for the measurement build (nvcc -DASZ_ENV_PROFILE, tools/env_profile.py); they compile to nothing otherwise.
@@ -113,11 +115,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   using SM = EnvSmem<SIDE, PITCHED>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
-  // smem: [per-CTA wall pattern][per warp: 2 staging buffers][per warp: board][per-CTA body-value table]
+  // smem: [per-CTA wall pattern][per warp: 2 staging buffers][per warp: 2 boards][per-CTA body-value table]
   float* s_bg = reinterpret_cast<float*>(smem_raw);
   float* stage0 = s_bg + SM::BG + warp * 2 * SM::WSTAGE;
-  uint16_t* sb = reinterpret_cast<uint16_t*>(s_bg + SM::BG + WARPS * 2 * SM::WSTAGE) + warp * G::PC;
-  float* s_lut = reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(s_bg + SM::BG + WARPS * 2 * SM::WSTAGE) + WARPS * G::PC);
+  uint16_t* sb = reinterpret_cast<uint16_t*>(s_bg + SM::BG + WARPS * 2 * SM::WSTAGE) + warp * 2 * G::PC;   // the ticket's two games
+  float* s_lut = reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(s_bg + SM::BG + WARPS * 2 * SM::WSTAGE) + WARPS * 2 * G::PC);
   for (int d = (int)threadIdx.x; d < G::PC + 8; d += WARPS * 32) s_lut[d] = (float)((double)d * 0.02);   // game.py:239, float64 product
   unsigned char* s_plut = reinterpret_cast<unsigned char*>(s_lut + G::PC + 8);
   if constexpr (PITCHED) fill_pitch_luts<G>(s_plut, (int)threadIdx.x, WARPS * 32);
@@ -150,19 +152,26 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
 #endif
   __syncwarp();
 
-  // dynamic scheduling: the first game of a warp is static, later ones come from a global counter that is fetched one
-  // game ahead; the next game's record is prefetched into registers while the current game's planes are encoded
+  // Dynamic scheduling in TICKETS of (mostly) two consecutive games.  The first ticket of a warp is static, later
+  // ones come from the kernel's scheduling word, which also hands out the batch rows: ONE atomicAdd per ticket takes the rows of
+  // both games and the warp's next ticket.  Why pairs: every one of these atomics hits the same 8-byte word, and an L2 slice
+  // serves same-address atomics one after the other at 2.3 - 3.6 ns each (which of the two depends on the slice the word is homed
+  // in and on the state of the L2, neither under the kernel's control): with one atomic per game, 65,536 games took 150 us or
+  // 236 us per launch -- exactly that serialisation -- whatever the rest of the kernel did; with two per game 360 us
+  // (profiles/r02_env_hot_word_scan.txt).  Flow per ticket: tic A, tic B, the atomic, then the planes of B (its snakes are still
+  // in registers) and of A (the boards stay in the warp's two board buffers, A's snake records in a 64-byte stash); the next
+  // ticket's first record is prefetched into registers while the planes are encoded, B's record while A is stepped.
   const int n_warps = (int)gridDim.x * WARPS;
   constexpr int BW = G::CPL / 2;                 // 32-bit words of board per lane
   uint32_t pf_board[BW];
   uint64_t pf_snake = 0;
   uint32_t pf_meta = 0;
-  // the caller's actions of the next game travel with its record (cp.async into a per-warp slot: no register held across
+  // the caller's actions of a game travel with its record (cp.async into a per-warp slot: no register held across
   // the encode), instead of being an exposed load inside the tic
   __shared__ __align__(8) uint8_t s_act[WARPS][2][8];
+  __shared__ uint64_t s_stash[WARPS][8];         // game A's snake records between its tic and its encode (game B's stay in registers)
   constexpr bool given_actions = ACTS;
-  int act_slot = 0;
-  int g = (int)blockIdx.x * WARPS + warp;
+  int pf_slot = 0, act_slot = 0;                 // slot the next prefetch writes / slot of the game being stepped
   const uint64_t keep = HINTS ? (p.hints == 2 ? l2_policy_evict_normal() : l2_policy_evict_last()) : 0ull;
   auto prefetch = [&](int gi) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cells + (size_t)gi * G::PC);
@@ -176,33 +185,28 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       if (lane < 8) { pf_snake = p.snakes[(size_t)gi * 8 + lane]; pf_meta = p.meta[(size_t)gi * 8 + lane]; }
     }
     if constexpr (given_actions) if (lane == 0) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\ncp.async.commit_group;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_act[warp][act_slot ^ 1][0])),
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\ncp.async.commit_group;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_act[warp][pf_slot][0])),
                    "l"(p.actions + (size_t)gi * 8)
                    : "memory");
     }
   };
-#if defined(ASZ_EXP_HALF_ATOM)
-  int exp_spare = 0, exp_row = 0, exp_nxt = 0;
-#endif
-  if (g < p.G) { prefetch(g); act_slot ^= 1; }
-  while (g < p.G) {
-    ASZ_PROF_DECL
-    int nxt = 0;
-    {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(sb);
+  // the prefetched record -> the board buffer `board`, the lanes' snake registers and the game counters
+  auto unpack = [&](uint16_t* board, Snake& sn, Meta& m) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(board);
 #pragma unroll
-      for (int q = 0; q < BW; ++q) dst[lane * BW + q] = pf_board[q];
-    }
-    Snake sn; sn.head = 0xFFFF; sn.len = 0; sn.health = 0; sn.last = 0; sn.alive = 0; sn.reward = 0;
+    for (int q = 0; q < BW; ++q) dst[lane * BW + q] = pf_board[q];
+    sn.head = 0xFFFF; sn.len = 0; sn.health = 0; sn.last = 0; sn.alive = 0; sn.reward = 0;
     if (lane < 8) sn = unpack_snake(pf_snake);
-    Meta m;
     m.turn = __shfl_sync(kFull, pf_meta, 0); m.episode = __shfl_sync(kFull, pf_meta, 1); m.wall = __shfl_sync(kFull, pf_meta, 2);
     m.body = __shfl_sync(kFull, pf_meta, 3); m.headc = __shfl_sync(kFull, pf_meta, 4); m.starve = __shfl_sync(kFull, pf_meta, 5);
     m.eaten = __shfl_sync(kFull, pf_meta, 6); m.flags = __shfl_sync(kFull, pf_meta, 7);
+    act_slot = pf_slot; pf_slot ^= 1;
     __syncwarp();
-    ASZ_PROF(0);   // waiting for the prefetched record
-    int row = 0, n_rows = 0;
-    unsigned live_mask = 0;
+  };
+  // one game: tic (results, in-place reset, record write-back) and its live snakes = the rows it needs
+  // `stash` (game A of a pair): where the lanes' packed snake records wait for the encode; `pf_rec`: the record as unpacked
+  auto step_game = [&](int g, uint16_t* board, Snake& sn, Meta& m, unsigned& live_mask, int& n_rows, uint64_t* stash, uint64_t pf_rec) {
+    live_mask = 0u; n_rows = 0;
     if ((p.flags & ASZ_STEP_TIC) && !(m.flags & 1u)) {
       int move = 1;
       uint32_t spawn_r[2] = {0u, 0u};
@@ -222,9 +226,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         if (lane < 8) move = (int)s_act[warp][act_slot][lane];
       }
       const int spawn_cell = (p.spawn_mode == ASZ_SPAWN_REPLAY) ? p.spawn_cells[g] : -1;
-      const TicResult r = warp_tic<G>(sb, sn, m, move, p.health_dec, p.spawn_mode, spawn_cell, p.chance_thresh, p.seed,
+      const TicResult r = warp_tic<G>(board, sn, m, move, p.health_dec, p.spawn_mode, spawn_cell, p.chance_thresh, p.seed,
                                       (uint32_t)g, p.S, merged_rng ? spawn_r : nullptr);
-      ASZ_PROF(1);   // draws + tic
       if (p.rewards != nullptr && lane < 8)
         p.rewards[(size_t)g * 8 + lane] = (int8_t)(sn.reward == 1 ? 1 : sn.reward == 2 ? -1 : 0);
       if (lane == 0) {
@@ -235,38 +238,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
           s_wtot[warp][4] += m.eaten; s_wtot[warp][5] += m.turn; s_wtot[warp][6] += 1u;
         }
       }
-      if (r.ended && (p.flags & ASZ_STEP_AUTO_RESET)) warp_init_native<G>(sb, sn, m, p.S, p.seed, (uint32_t)g, m.episode + 1);
-      // rows of this game and the next game of this warp: one atomicAdd, issued before the write-back so that its latency is covered
-      if (enc && !(m.flags & 1u)) {
-        live_mask = __ballot_sync(kFull, sn.alive != 0);
-        n_rows = __popc(live_mask);
-      }
-      if (lane == 0) {
-#if defined(ASZ_EXP_HALF_ATOM)      // timing experiment only (rows are NOT compact): one atomic per ASZ_EXP_HALF_ATOM games
-        if (exp_spare > 0) { row = exp_row; nxt = exp_nxt; exp_row += 4; exp_nxt += 1; exp_spare -= 1; }
-        else {
-          constexpr int NB = ASZ_EXP_HALF_ATOM;
-          const unsigned long long t = atomicAdd(p.sched, ((unsigned long long)NB << 32) | (unsigned long long)(unsigned)(n_rows + 4 * (NB - 1)));
-          row = (int)(uint32_t)t; nxt = n_warps + (int)(t >> 32);
-          exp_row = row + n_rows; exp_nxt = nxt + 1; exp_spare = NB - 1;
-        }
-#elif defined(ASZ_EXP_ATOM_HINT)    // experiment: the hot line carries the evict_last policy
-        unsigned long long t;
-        asm volatile("atom.global.add.L2::cache_hint.u64 %0, [%1], %2, %3;" : "=l"(t) : "l"(p.sched), "l"((1ull << 32) | (unsigned long long)(unsigned)n_rows), "l"(l2_policy_evict_last()) : "memory");
-        row = (int)(uint32_t)t; nxt = n_warps + (int)(t >> 32);
-#else
-        const unsigned long long t = atomicAdd(p.sched, (1ull << 32) | (unsigned long long)(unsigned)n_rows);
-        row = (int)(uint32_t)t; nxt = n_warps + (int)(t >> 32);
-#if defined(ASZ_EXP_DOUBLE_ATOM)    // timing experiment: a second returning atomic on the same word per game
-        row += (int)(atomicAdd(p.sched, 0ull) >> 63);
-#endif
-#endif
-        s_wtot[warp][8] += (uint32_t)n_rows;
-      }
+      if (r.ended && (p.flags & ASZ_STEP_AUTO_RESET)) warp_init_native<G>(board, sn, m, p.S, p.seed, (uint32_t)g, m.episode + 1);
       // write the record back
       {
         uint32_t* gc = reinterpret_cast<uint32_t*>(p.cells + (size_t)g * G::PC);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(sb);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(board);
         if constexpr (BW % 2 == 0) {
 #pragma unroll
           for (int q = 0; q < BW / 2; ++q) {
@@ -285,74 +261,111 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       if (lane < 8) {
         const uint32_t mv = lane == 0 ? m.turn : lane == 1 ? m.episode : lane == 2 ? m.wall : lane == 3 ? m.body
                           : lane == 4 ? m.headc : lane == 5 ? m.starve : lane == 6 ? m.eaten : m.flags;
+        const uint64_t rec = pack_snake(sn);
+        if (stash != nullptr) stash[lane] = rec;
         if constexpr (HINTS) {
-          st_hint_u64(p.snakes + (size_t)g * 8 + lane, pack_snake(sn), keep);
+          st_hint_u64(p.snakes + (size_t)g * 8 + lane, rec, keep);
           st_hint_u32(p.meta + (size_t)g * 8 + lane, mv, keep);
         } else {
-          p.snakes[(size_t)g * 8 + lane] = pack_snake(sn);
+          p.snakes[(size_t)g * 8 + lane] = rec;
           p.meta[(size_t)g * 8 + lane] = mv;
         }
       }
     } else {
       if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) p.ended[g] = 0;
-      if (enc && !(m.flags & 1u)) {
-        live_mask = __ballot_sync(kFull, sn.alive != 0);
-        n_rows = __popc(live_mask);
-      }
-      if (lane == 0) {
-        const unsigned long long t = atomicAdd(p.sched, (1ull << 32) | (unsigned long long)(unsigned)n_rows);
-        row = (int)(uint32_t)t; nxt = n_warps + (int)(t >> 32);
-        s_wtot[warp][8] += (uint32_t)n_rows;
-      }
+      if (stash != nullptr && lane < 8) stash[lane] = pf_rec;      // not stepped: the record as it was loaded
     }
-    ASZ_PROF(2);   // results, reset, row atomic issue, record write-back
-    // the next game's record streams in while this game's planes are encoded
-    nxt = __shfl_sync(kFull, nxt, 0);
-    if (nxt < p.G) prefetch(nxt);
-    ASZ_PROF(3);   // waiting for the work counter, issuing the prefetch
-    // ---- planes of this game (rows of a game stay contiguous, ascending snake id) ----
-    {
-      if (n_rows > 0) {
-        CellView<G> cv;
-        warp_cell_view<G>(sb, sn, cv, s_lut);
-        row = __shfl_sync(kFull, row, 0) + p.row_base;
-        ASZ_PROF(4);   // cell view, waiting for the row atomic
-        unsigned rest = live_mask;
-        if constexpr (PITCHED) {
-          rest = 0u;
-          const int n_emit = min(n_rows, p.max_rows - row);
-          if (n_emit > 0) {
-            float* gbase = p.planes + (size_t)row * PitchGeo<G>::PITCH;
+    if (enc && !(m.flags & 1u)) {
+      live_mask = __ballot_sync(kFull, sn.alive != 0);
+      n_rows = __popc(live_mask);
+    }
+  };
+  // planes of one game into rows [row, row + n_rows) (rows of a game stay contiguous, ascending snake id)
+  auto encode_game = [&](int g, const uint16_t* board, const Snake& sn, unsigned live_mask, int n_rows, int row) {
+    if (n_rows <= 0) return;
+    CellView<G> cv;
+    warp_cell_view<G>(board, sn, cv, s_lut);
+    unsigned rest = live_mask;
+    if constexpr (PITCHED) {
+      rest = 0u;
+      const int n_emit = min(n_rows, p.max_rows - row);
+      if (n_emit > 0) {
+        float* gbase = p.planes + (size_t)row * PitchGeo<G>::PITCH;
 #ifdef ASZ_ENC_V3A       // A/B: the first pitched encode (per-lane restore bookkeeping, select chains, float64 products per plane)
-            if (p.flags & ASZ_STEP_KEYS) warp_encode_game_v3<G, true, HINTS>(cv, sn, live_mask, n_emit, ctx, gbase, p.keys + 2 * (size_t)row, p.row_ids + row, g * 8);
-            else warp_encode_game_v3<G, false, HINTS>(cv, sn, live_mask, n_emit, ctx, gbase, nullptr, p.row_ids + row, g * 8);
+        if (p.flags & ASZ_STEP_KEYS) warp_encode_game_v3<G, true, HINTS>(cv, sn, live_mask, n_emit, ctx, gbase, p.keys + 2 * (size_t)row, p.row_ids + row, g * 8);
+        else warp_encode_game_v3<G, false, HINTS>(cv, sn, live_mask, n_emit, ctx, gbase, nullptr, p.row_ids + row, g * 8);
 #else
-            if (p.flags & ASZ_STEP_KEYS) warp_encode_game_v3b<G, true, HINTS>(cv, sn, live_mask, n_emit, ctxp, gbase, p.keys + 2 * (size_t)row, p.row_ids + row, g * 8);
-            else warp_encode_game_v3b<G, false, HINTS>(cv, sn, live_mask, n_emit, ctxp, gbase, nullptr, p.row_ids + row, g * 8);
+        if (p.flags & ASZ_STEP_KEYS) warp_encode_game_v3b<G, true, HINTS>(cv, sn, live_mask, n_emit, ctxp, gbase, p.keys + 2 * (size_t)row, p.row_ids + row, g * 8);
+        else warp_encode_game_v3b<G, false, HINTS>(cv, sn, live_mask, n_emit, ctxp, gbase, nullptr, p.row_ids + row, g * 8);
 #endif
-          }
-        }
-        while (rest) {
-          const int vs = __ffs(rest) - 1;
-          rest &= rest - 1;
-          if (row < p.max_rows) {
-            uint64_t k0 = 0, k1 = 0;
-            if (p.flags & ASZ_STEP_KEYS) {
-              warp_encode_v2<G, true, HINTS>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, &k0, &k1);
-              if (lane == 0) { p.keys[2 * (size_t)row] = k0; p.keys[2 * (size_t)row + 1] = k1; }
-            } else {
-              warp_encode_v2<G, false, HINTS>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
-            }
-            if (lane == 0) p.row_ids[row] = g * 8 + vs;
-          }
-          ++row;
-        }
       }
     }
-    __syncwarp();   // the board buffer is reused by the next game
+    while (rest) {
+      const int vs = __ffs(rest) - 1;
+      rest &= rest - 1;
+      if (row < p.max_rows) {
+        uint64_t k0 = 0, k1 = 0;
+        if (p.flags & ASZ_STEP_KEYS) {
+          warp_encode_v2<G, true, HINTS>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, &k0, &k1);
+          if (lane == 0) { p.keys[2 * (size_t)row] = k0; p.keys[2 * (size_t)row + 1] = k1; }
+        } else {
+          warp_encode_v2<G, false, HINTS>(cv, sn, vs, ctx, p.planes, (size_t)row * G::PLANE, nullptr, nullptr);
+        }
+        if (lane == 0) p.row_ids[row] = g * 8 + vs;
+      }
+      ++row;
+    }
+  };
+
+  // tickets [0, T1) are pairs (games 2t, 2t + 1), tickets [T1, NT) the last games one by one: a warp that draws its last ticket
+  // late holds up the launch by one ticket, so the end of the launch is handed out in single games
+  const int T1 = p.pair_tickets, NT = p.n_tickets;
+  auto first_game = [&](int tk) { return tk < T1 ? 2 * tk : tk + T1; };
+  int t = (int)blockIdx.x * WARPS + warp;
+  if (t < NT) prefetch(first_game(t));
+  while (t < NT) {
+    ASZ_PROF_DECL
+    const int gA = first_game(t);
+    const int cnt = t < T1 ? 2 : 1;
+    Snake sn; Meta m;
+    unsigned maskA = 0u, maskB = 0u;
+    int nA = 0, nB = 0;
+#pragma unroll 1
+    for (int h = 0; h < cnt; ++h) {               // one copy of the tic in the instruction stream, two trips
+      uint16_t* board = sb + h * G::PC;
+      const uint64_t rec0 = pf_snake;
+      unpack(board, sn, m);
+      if (h == 0) { ASZ_PROF(0); }                // waiting for the prefetched record
+      if (h + 1 < cnt) prefetch(gA + 1);          // B's record streams in while A is stepped
+      unsigned mk; int nk;
+      step_game(gA + h, board, sn, m, mk, nk, (h + 1 < cnt) ? &s_stash[warp][0] : nullptr, rec0);
+      if (h == 0) { maskA = mk; nA = nk; } else { maskB = mk; nB = nk; }
+    }
+    ASZ_PROF(1);   // draws, tics, results, record write-backs
+    int row = 0, nxt = 0;
+    if (lane == 0) {
+      const unsigned long long v = atomicAdd(p.sched, (1ull << 32) | (unsigned long long)(unsigned)(nA + nB));
+      row = (int)(uint32_t)v; nxt = n_warps + (int)(v >> 32);
+      s_wtot[warp][8] += (uint32_t)(nA + nB);
+    }
+    // the next ticket's first record streams in while this ticket's planes are encoded
+    nxt = __shfl_sync(kFull, nxt, 0);
+    ASZ_PROF(2);   // waiting for the scheduling word
+    if (nxt < NT) prefetch(first_game(nxt));
+    ASZ_PROF(3);   // issuing the prefetch
+    row = __shfl_sync(kFull, row, 0) + p.row_base;
+    // the last game stepped is still in the snake registers: its planes first, then game A's from the stash
+#pragma unroll 1
+    for (int h = cnt - 1; h >= 0; --h) {
+      if (h + 1 < cnt) {
+        __syncwarp();
+        if (lane < 8) sn = unpack_snake(s_stash[warp][lane]);
+      }
+      encode_game(gA + h, sb + h * G::PC, sn, h ? maskB : maskA, h ? nB : nA, (h + 1 < cnt) ? row + nB : row);
+    }
+    __syncwarp();   // the board buffers are reused by the next ticket
     ASZ_PROF(5);   // plane encode (ASZ_PROF 6 inside: waiting for the copy engine to release a staging buffer)
-    act_slot ^= 1;
-    g = nxt;
+    t = nxt;
   }
   if (lane == 0) {
     bulk_wait_read<0>();   // shared memory must stay valid until the copy engine has read it
@@ -382,12 +395,9 @@ __global__ void __launch_bounds__(WARPS * 32) env_reset_kernel(uint16_t* cells, 
   store_meta(meta + (size_t)g * 8, m, lane);
 }
 
-// ---- L2 conditioning ------------------------------------------------------------------------------------------------
-// env_step_kernel streams ~1 GB of planes per launch through a 126 MB L2 and runs in one of two stable regimes:
-// ~150 us per launch when the L2's normal-priority lines are CLEAN (the evict_first plane lines then form a small pool that
-// is written back as fast as it is filled), ~220 us when the L2 is full of dirty lines (after bulk initialisation, after
-// another kernel streamed writes through it, after encode-only launches, whose store rate exceeds what HBM drains).  The L2
-// does not clean itself when idle; reading more than ~8x its capacity does.  This kernel is that read sweep.
+// ---- L2 read sweep (experiments) --------------------------------------------------------------------------------------
+// Reads ~1.25 GB, which leaves the L2 full of clean lines.  With one atomic per game the state of the L2 decided how fast the
+// slice of the kernel's hot word served its atomics (tools/env_hot.py reproduces the scan); the ticket kernel does not care.
 __global__ void __launch_bounds__(256) l2_sweep_kernel(const uint4* __restrict__ p, size_t n, int passes, unsigned long long* sink) {
   unsigned long long acc = 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -413,7 +423,7 @@ struct EnvLaunch {
   template <bool PITCHED>
   static size_t smem_bytes() {
     using SM = EnvSmem<SIDE, PITCHED>;
-    return (size_t)(SM::BG + WARPS * 2 * SM::WSTAGE) * sizeof(float) + (size_t)WARPS * G::PC * sizeof(uint16_t) +
+    return (size_t)(SM::BG + WARPS * 2 * SM::WSTAGE) * sizeof(float) + (size_t)WARPS * 2 * G::PC * sizeof(uint16_t) +
            (size_t)(G::PC + 8) * sizeof(float) + (size_t)SM::LUT_BYTES;
   }
   template <int MINB, bool HINTS, bool ACTS, bool PITCHED>
@@ -440,7 +450,13 @@ struct EnvLaunch {
       }
     }
     const int blocks = std::min((p.G + WARPS - 1) / WARPS, p.n_sm * MINB);
-    env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS, PITCHED><<<blocks, WARPS * 32, smem_bytes<PITCHED>(), st>>>(p);
+    // the last `rounds` games of every warp are handed out one by one, everything before in pairs
+    static int rounds = -1;
+    if (rounds < 0) { const char* v = getenv("ASZ_ENV_TAIL_ROUNDS"); rounds = v ? std::max(0, atoi(v)) : 2; }
+    EnvParams q = p;
+    q.pair_tickets = std::max(0, p.G - rounds * blocks * WARPS) / 2;
+    q.n_tickets = p.G - q.pair_tickets;
+    env_step_kernel<SIDE, WARPS, MINB, HINTS, ACTS, PITCHED><<<blocks, WARPS * 32, smem_bytes<PITCHED>(), st>>>(q);
     return cuda_ok(cudaGetLastError(), "env_step_kernel launch") ? ASZ_OK : ASZ_ERR_CUDA;
   }
   static int step(const EnvParams& p, cudaStream_t st) {
@@ -497,9 +513,6 @@ static int pc_of(int side) { return side == 7 ? Geo<7>::PC : side == 11 ? Geo<11
 static size_t hot_word_offset(int k) {
   return ((size_t)k * 4096 + (size_t)(k % 29) * 128 + (size_t)(k % 3) * ((size_t)1 << 21)) % (((size_t)8 << 20) - 128);
 }
-static bool streams_through_l2(const asz_engine* e) {
-  return e->auto_condition && (size_t)e->cfg.games * e->cfg.snakes * e->pitch * sizeof(float) >= ((size_t)192 << 20);
-}
 
 }  // namespace asz
 
@@ -515,11 +528,6 @@ static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   e->cfg = *cfg;
   { const char* v = getenv("ASZ_ENV_HINTS"); e->device_hints = v ? atoi(v) : 1; }            // experiments only
   { const char* v = getenv("ASZ_ENV_HINTS_HOST"); e->host_hints = v ? atoi(v) : 1; }
-  { const char* v = getenv("ASZ_AUTO_CONDITION"); e->auto_condition = v ? atoi(v) : 1; }
-  { const char* v = getenv("ASZ_L2_SLOW_GBS"); if (v) e->l2_slow_gbs = atof(v); }
-  ASZ_CUDA(cudaEventCreate(&e->l2mon.ev0));
-  ASZ_CUDA(cudaEventCreate(&e->l2mon.ev1));
-  ASZ_CUDA(cudaMallocHost(&e->l2mon.h_rows, sizeof(int32_t)));
   e->step_hints = e->device_hints;
   ASZ_CUDA(cudaGetDevice(&e->device));
   ASZ_CUDA(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, e->device));
@@ -583,9 +591,6 @@ int asz_engine_destroy(asz_engine* e) {
   records_destroy(e);
   host_pipe_destroy(e);
   gameset_free(e->root);
-  if (e->l2mon.ev0) cudaEventDestroy(e->l2mon.ev0);
-  if (e->l2mon.ev1) cudaEventDestroy(e->l2mon.ev1);
-  if (e->l2mon.h_rows) cudaFreeHost(e->l2mon.h_rows);
   cudaFree(e->planes); cudaFree(e->row_ids); cudaFree(e->row_count); cudaFree(e->actions); cudaFree(e->spawn_cells);
   cudaFree(e->ended); cudaFree(e->rewards); cudaFree(e->totals);
   delete e;
@@ -601,64 +606,10 @@ static int reset_games(asz_engine* e, cudaStream_t st) {
   }
 }
 
-// Picks the address of the kernel's hot word for THIS process (engines whose batch streams through the L2 only): for each
-// candidate, one L2 sweep and a few real tic + encode launches on the freshly initialised games into the engine's own plane
-// buffer, timed with events; the first candidate that shows the fast regime wins (about every second one does), otherwise the
-// best.  The caller re-initialises the games afterwards.  ~3 ms per candidate, once per asz_reset.
-static int select_hot_word(asz_engine* e, cudaStream_t st) {
-  asz_engine::L2Monitor& mon = e->l2mon;
-  const int saved = e->auto_condition;
-  asz_step_args a;
-  memset(&a, 0, sizeof a);
-  a.flags = ASZ_STEP_TIC | ASZ_STEP_ENCODE | ASZ_STEP_AUTO_RESET | ASZ_STEP_RANDOM_ACT; a.spawn_mode = ASZ_SPAWN_NATIVE;
-  a.d_planes = e->planes; a.d_row_ids = e->row_ids; a.max_rows = e->cfg.games * e->cfg.snakes; a.plane_pitch = e->pitch;
-  double best = 0.0;
-  int best_k = mon.candidate, rc = ASZ_OK;
-  for (int trial = 0; trial < 12 && rc == ASZ_OK; ++trial) {
-    const int k = mon.candidate + trial;
-    e->sched_off = hot_word_offset(k);
-    a.d_row_count = e->rows_ptr();
-    e->auto_condition = saved;                      // asz_condition_l2 is a no-op when conditioning is off
-    rc = asz_condition_l2(e, st);
-    e->auto_condition = 0;                          // no monitor inside the probe launches
-    for (int i = 0; i < 3 && rc == ASZ_OK; ++i) rc = asz_env_step(e, &a, st);
-    if (rc != ASZ_OK) break;
-    cudaEventRecord(mon.ev0, st);
-    for (int i = 0; i < 6 && rc == ASZ_OK; ++i) rc = asz_env_step(e, &a, st);
-    cudaMemcpyAsync(mon.h_rows, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-    cudaEventRecord(mon.ev1, st);
-    if (cudaEventSynchronize(mon.ev1) != cudaSuccess) { rc = ASZ_ERR_CUDA; break; }
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, mon.ev0, mon.ev1);
-    const double gbs = ms > 0.0f ? (double)*mon.h_rows * e->pitch * sizeof(float) * 6.0 / (ms * 1e-3) / 1e9 : 0.0;
-    if (gbs > best) { best = gbs; best_k = k; }
-    if (gbs >= e->l2_slow_gbs * 1.06) break;        // clearly the fast regime
-  }
-  e->auto_condition = saved;
-  const bool ended_on_best = hot_word_offset(best_k) == e->sched_off;
-  mon.candidate = best_k;
-  e->sched_off = hot_word_offset(best_k);
-  mon.last_gbs = best; mon.fails = 0; mon.pending = false; mon.since_sample = 0; mon.cooldown = 0;
-  // the probe's last launches ran in the fast regime on the chosen word: the L2 is conditioned already (re-initialising the games
-  // writes 23 MB, which does not disturb it); otherwise the first tic + encode launch starts with a sweep
-  e->l2_dirty = !(ended_on_best && best >= e->l2_slow_gbs * 1.06);
-  return rc;
-}
-
 int asz_reset(asz_engine* e, void* stream) {
   if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = reset_games(e, st);
-  if (rc != ASZ_OK) return rc;
-  if (streams_through_l2(e) && !e->hot_word_selected) {
-    rc = select_hot_word(e, st);
-    if (rc != ASZ_OK) return rc;
-    e->hot_word_selected = true;
-    return reset_games(e, st);                      // the probe stepped the games: start them again
-  }
-  e->l2_dirty = true;      // bulk initialisation usually leaves the L2 dirty
-  return ASZ_OK;
+  return reset_games(e, (cudaStream_t)stream);
 }
 
 int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
@@ -693,48 +644,6 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals; p.prof = e->totals + 16;
   p.sched = reinterpret_cast<unsigned long long*>(e->rows_ptr());   // low word = the row count the callers read
   p.hints = e->step_hints;
-  // "L2 conditioning": streaming launches (tic + encode into pitched rows of an engine whose batch is much larger than the L2)
-  const bool streaming = (a->flags & ASZ_STEP_TIC) && (a->flags & ASZ_STEP_ENCODE) && p.pitched && streams_through_l2(e);
-  asz_engine::L2Monitor& mon = e->l2mon;
-  bool sample = false;
-  if (streaming) {
-    if (mon.pending && cudaEventQuery(mon.ev1) == cudaSuccess) {       // an earlier sample has finished: which regime was it in?
-      float ms = 0.0f;
-      mon.pending = false;
-      if (cudaEventElapsedTime(&ms, mon.ev0, mon.ev1) == cudaSuccess && ms > 0.0f) {
-        const double bytes = (double)*mon.h_rows * e->pitch * sizeof(float);
-        if (bytes >= (double)((size_t)192 << 20)) {
-          mon.last_gbs = bytes / (ms * 1e-3) / 1e9;
-          mon.samples += 1;
-          // launches of asz_env_step_host also post their per-game results to pinned host memory: a lower bar for them
-          if (mon.last_gbs < e->l2_slow_gbs * (mon.pending_host ? 0.9 : 1.0)) { mon.slow_samples += 1; mon.fails += 1; e->l2_dirty = true; }
-          else mon.fails = 0;
-        }
-      }
-    }
-    cudaGetLastError();                                                 // cudaErrorNotReady of the query is not an error
-    if (mon.cooldown > 0) mon.cooldown -= 1;
-    if (e->l2_dirty && mon.cooldown == 0) {
-      if (mon.fails >= 2 && mon.rotations < 24) {
-        // two sweeps in a row did not help: the hot word sits in an L2 slice from which the fast regime cannot be reached.  Move
-        // it to the next candidate address (other address bits 7..22 => another slice); about every second candidate is good.
-        mon.candidate += 1; mon.rotations += 1; mon.fails = 0;
-        e->sched_off = hot_word_offset(mon.candidate);
-        p.sched = reinterpret_cast<unsigned long long*>(e->rows_ptr());
-        p.row_count = e->rows_ptr();
-      }
-      if (mon.fails >= 4) { mon.cooldown = 4096; mon.fails = 0; e->l2_dirty = false; }   // nothing helps here: stop trying for a while
-      else {
-        const int rc0 = asz_condition_l2(e, stream);
-        if (rc0 != ASZ_OK) return rc0;
-        mon.sweeps += 1;
-        mon.since_sample = 5;                                           // look at the result soon
-      }
-    }
-    if (!mon.pending && ++mon.since_sample >= 8) { sample = true; mon.since_sample = 0; mon.pending_host = e->host_step; }
-  }
-  if ((a->flags & ASZ_STEP_ENCODE) && !(a->flags & ASZ_STEP_TIC)) e->l2_dirty = true;   // encode-only launches out-run the HBM drain
-  if (sample) ASZ_CUDA(cudaEventRecord(mon.ev0, st));
   ASZ_CUDA(cudaMemsetAsync(p.sched, 0, sizeof(unsigned long long), st));
   int rc;
   switch (e->cfg.side) {
@@ -743,11 +652,6 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
     default: rc = EnvLaunch<19>::step(p, st); break;
   }
   if (rc != ASZ_OK) return rc;
-  if (sample) {
-    ASZ_CUDA(cudaMemcpyAsync(mon.h_rows, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    ASZ_CUDA(cudaEventRecord(mon.ev1, st));
-    mon.pending = true;
-  }
   if (a->d_row_count && a->d_row_count != e->rows_ptr())
     ASZ_CUDA(cudaMemcpyAsync(a->d_row_count, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return ASZ_OK;
@@ -838,9 +742,7 @@ int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const
     if (void* d = pinned_alias(h_rewards)) { a.d_rewards = static_cast<int8_t*>(d); zc_rewards = true; }
   }
   e->step_hints = e->host_hints;
-  e->host_step = true;
   const int rc = asz_env_step(e, &a, stream);
-  e->host_step = false;
   e->step_hints = e->device_hints;
   if (rc != ASZ_OK) return rc;
   if (h_ended && !zc_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, e->ended, G, cudaMemcpyDeviceToHost, st));
@@ -891,13 +793,11 @@ int asz_condition_l2(asz_engine* e, void* stream) {
   if (!e) { set_error("null engine"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
   const size_t bytes = (size_t)e->cfg.games * e->cfg.snakes * e->pitch * sizeof(float);
-  e->l2_dirty = false;
   if (bytes < ((size_t)192 << 20)) return ASZ_OK;      // a batch that fits the L2 does not stream through it: nothing to condition
   const size_t want = (size_t)5 << 28;                 // 1.25 GB of read traffic (8x the L2 is what the experiments needed)
   const int passes = (int)((want + bytes - 1) / bytes);
   l2_sweep_kernel<<<e->n_sm * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(e->planes), bytes / 16, passes, e->totals + 31);
   if (!cuda_ok(cudaGetLastError(), "l2_sweep_kernel")) return ASZ_ERR_CUDA;
-  e->l2_dirty = false;
   return ASZ_OK;
 }
 
@@ -906,8 +806,6 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals) {
   DeviceGuard guard(e->device);
   ASZ_CUDA(cudaDeviceSynchronize());
   ASZ_CUDA(cudaMemcpy(h_totals, e->totals, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  h_totals[9] = e->l2mon.sweeps; h_totals[10] = e->l2mon.samples; h_totals[11] = e->l2mon.slow_samples;   // host-side: L2 monitor
-  h_totals[12] = (uint64_t)e->l2mon.last_gbs; h_totals[13] = e->l2mon.rotations;
   return ASZ_OK;
 }
 
@@ -925,9 +823,7 @@ int asz_internal_set_hot_word(asz_engine* e, int32_t k) {
   if (!e || k < 0) { set_error("bad argument"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
   ASZ_CUDA(cudaDeviceSynchronize());
-  e->l2mon.candidate = k;
   e->sched_off = hot_word_offset(k);
-  e->hot_word_selected = true;
   return ASZ_OK;
 }
 int asz_internal_state(asz_engine* e, void** d_ptrs) {

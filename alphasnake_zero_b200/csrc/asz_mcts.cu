@@ -639,7 +639,6 @@ int asz_search_begin(asz_engine* e, void* stream) {
   SearchState* s = e->search;
   if (s->open) { set_error("asz_search_begin: a search is already open"); return ASZ_ERR_STATE; }
   (void)stream;
-  e->l2_dirty = true;  // the search and the network stream through the L2 (see asz_engine::l2_dirty)
   s->root_turn += 1;   // agent.py:30-31: every entry ages by one
   s->epoch = -1; s->step = 0; s->open = true;
   return ASZ_OK;

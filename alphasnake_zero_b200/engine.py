@@ -152,15 +152,13 @@ class Engine:
         return rows.value
 
     def condition_l2(self):
-        """one read sweep that leaves the L2 full of clean lines: the fast regime of the fused tic + encode kernel on engines whose
-        batch is much larger than the L2 (asz_condition_l2; a no-op for small engines)"""
+        """experiments (tools/env_hot.py): one read sweep that leaves the L2 full of clean lines"""
         check(self.L.asz_condition_l2(self.h, self.stream))
 
     def totals(self):
         t = np.zeros(16, np.uint64)
         check(self.L.asz_get_totals(self.h, _np(t)))
-        return dict(zip(("wall", "body", "head", "starve", "food_eaten", "game_length", "episodes", "tics", "planes",
-                         "l2_sweeps", "l2_samples", "l2_slow_samples", "l2_last_gbs", "l2_rotations"), t.tolist()))
+        return dict(zip(("wall", "body", "head", "starve", "food_eaten", "game_length", "episodes", "tics", "planes"), t.tolist()))
 
     # ---- convenience used by tests and the drop-in classes -------------------------------------------------------
     def rows(self):

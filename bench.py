@@ -409,9 +409,6 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     K, W = args.steps, max(args.warmup, 3)
-    # The engine is created BEFORE the NCCL communicator: the fused kernel's fast regime depends on where the engine's buffers
-    # land in device memory, and a large live allocation made before them (NCCL's buffers, any >= 256 MB tensor) leaves it in the
-    # slow one for good (tools/env_bisect.py); allocations made afterwards do not matter.
     eng = Engine(side=SIDE, snakes=SNAKES, health_dec=HEALTH_DEC, food_chance=CHANCE, games=GAMES, seed=1000 + rank)
     eng.reset()
     _ = eng.planes
@@ -425,18 +422,6 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- leg 1: device-resident throughput ("value") and the kernel roofline -----------------------------------
-    # engine settle (untimed, before the W warm-up steps): step until the engine's own L2 monitor has seen the fast regime twice in a
-    # row (it samples every 8th launch and re-conditions the L2 / moves its scheduling word when a sample is slow)
-    settle, good = 0, 0
-    last_samples = eng.totals()["l2_samples"]
-    while settle < 160 and good < 2:
-        for _ in range(8):
-            eng.step(**kw)
-        settle += 8
-        tt = eng.totals()                       # synchronises
-        if tt["l2_samples"] > last_samples:
-            good = good + 1 if tt["l2_last_gbs"] >= 5800 else 0
-            last_samples = tt["l2_samples"]
     for _ in range(W):
         eng.step(**kw)
     barrier()
@@ -670,8 +655,7 @@ def run_ours(args, rank, world, local_rank):
                    "games_per_gpu": GAMES, "planes_per_step": planes_all / max(steps_all, 1),
                    "l2": "each launch writes %.0f MB of planes (> 126 MB L2); the 21 MB of game records may stay L2 resident"
                          % (bytes_per_launch / 1e6),
-                   "plane_layout": "fp32 NHWC rows, 5,312 B apart (asz_plane_pitch: 5,292 B plane + 20 B pad, 32-byte aligned rows)",
-                   "engine_settle_launches": settle},
+                   "plane_layout": "fp32 NHWC rows, 5,312 B apart (asz_plane_pitch: 5,292 B plane + 20 B pad, 32-byte aligned rows)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "env_step_kernel (pitched rows, warp_encode_game_v3b)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_launch,
@@ -684,7 +668,6 @@ def run_ours(args, rank, world, local_rank):
                 "synchronous": {"value": e2e_sync_steps_all / (e2e_sync_ms * 1e-3), "unit": UNIT,
                                 "note": "asz_env_step_host: one blocking call per step (copy in, launch, results out, wait)"}},
         "gpu_launches": K, "clocks": clocks, "launch_us": launch_us,
-        "l2_monitor": {k: t_after[k] for k in ("l2_sweeps", "l2_samples", "l2_slow_samples", "l2_last_gbs", "l2_rotations")},
     }
     if planes_to_host is not None:
         out["e2e_planes_to_host"] = planes_to_host

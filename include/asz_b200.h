@@ -138,19 +138,9 @@ int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const
                         const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, void* stream, int32_t* ticket);
 int asz_env_wait_host(asz_engine* e, int32_t ticket, int32_t* h_row_count);
 
-/* Optional conditioning of the L2 before a long run of asz_env_step launches on a large engine (a batch much larger than the
- * L2): one read sweep of ~1.25 GB over the engine's plane buffer, which leaves the L2 full of clean lines.  The fused kernel
- * then runs in its fast regime (~150 us instead of ~220 us per 65,536-game launch) until something else streams writes
- * through the L2.  A no-op for engines whose batch fits the L2.  Enqueues one kernel on `stream`.
- * asz_env_step calls it by itself before a tic + encode launch whenever the engine's OWN work has dirtied the L2 since the
- * last sweep (asz_reset, encode-only launches, a search); call it explicitly after other kernels of the application
- * have streamed writes through the L2 (e.g. a large fill or copy on the same GPU). */
-int asz_condition_l2(asz_engine* e, void* stream);
-
 /* Running totals over games that ended since the last asz_reset (mp_game_runner.py:56-61, 71-76 divides by G):
  * h_totals[16] = wall, body, head, starve, food_eaten, game_length, episodes_finished, tics_executed, planes_written,
- * then the L2 monitor of asz_env_step (conditioning sweeps run, launches sampled, samples found in the slow regime, GB/s of
- * the last sample, times the kernel's hot scheduling word was moved to another address), then 2 reserved slots.  Synchronous. */
+ * then 7 reserved slots (0).  Synchronous. */
 int asz_get_totals(asz_engine* e, uint64_t* h_totals);
 
 /* device pointers of the packed root-game records, read-only for callers: d_ptrs[0] = cells (u16 [G][padded cells]),
@@ -162,8 +152,10 @@ int asz_get_totals(asz_engine* e, uint64_t* h_totals);
  * the last call, h_cycles[8] = record wait, tic, write-back, work-counter wait + prefetch, cell view + row wait, encode,
  * staging-buffer wait (inside encode), unused; all zero in the product build.  Synchronous. */
 int asz_internal_profile(asz_engine* e, uint64_t* h_cycles);
-/* experiments only (tools/env_hot.py): pins the fused kernel's scheduling word to the k-th candidate address */
+/* experiments only (tools/env_hot.py): the fused kernel's scheduling word at the k-th candidate address of its
+ * buffer (another L2 slice), and one read sweep of ~1.25 GB over the engine's plane buffer (leaves the L2 full of clean lines) */
 int asz_internal_set_hot_word(asz_engine* e, int32_t k);
+int asz_condition_l2(asz_engine* e, void* stream);
 int asz_internal_state(asz_engine* e, void** d_ptrs);
 /* device pointer of the engine's internal plane buffer (capacity G*S rows, asz_plane_pitch() floats apart) and row-id buffer */
 float* asz_internal_planes(asz_engine* e);
