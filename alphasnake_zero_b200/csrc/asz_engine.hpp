@@ -81,10 +81,15 @@ struct asz_engine {
   struct HostPipe {
     bool ready = false;
     cudaStream_t copy = nullptr;                 // host -> device copies of the steps' inputs
+    cudaStream_t copy_out = nullptr;             // device -> host copies of the steps' results
     cudaEvent_t copied[2] = {nullptr, nullptr};  // slot's inputs are on the device
+    cudaEvent_t stepped[2] = {nullptr, nullptr}; // slot's launch has finished
     cudaEvent_t done[2] = {nullptr, nullptr};    // slot's launch and result copies have finished
     uint8_t* actions[2] = {nullptr, nullptr};    // [G*8] per slot
     int32_t* spawn[2] = {nullptr, nullptr};      // [G] per slot
+    uint8_t* d_ended[2] = {nullptr, nullptr};    // [G] per slot: the kernel's per-game results before they travel
+    int8_t* d_rewards[2] = {nullptr, nullptr};   // [G*8] per slot
+    int32_t* d_rows[2] = {nullptr, nullptr};     // the step's row count
     int32_t* h_rows = nullptr;                   // pinned, one 64-byte line per slot
     bool busy[2] = {false, false};
     int next = 0;

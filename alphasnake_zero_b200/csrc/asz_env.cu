@@ -272,7 +272,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         }
       }
     } else {
-      if ((p.flags & ASZ_STEP_TIC) && lane == 0 && p.ended != nullptr) p.ended[g] = 0;
+      if (p.flags & ASZ_STEP_TIC) {     // a finished game is not stepped: its results of this tic are "nothing happened"
+        if (lane == 0 && p.ended != nullptr) p.ended[g] = 0;
+        if (lane < 8 && p.rewards != nullptr) p.rewards[(size_t)g * 8 + lane] = 0;
+      }
       if (stash != nullptr && lane < 8) stash[lane] = pf_rec;      // not stepped: the record as it was loaded
     }
     if (enc && !(m.flags & 1u)) {
@@ -667,12 +670,17 @@ static int host_pipe_create(asz_engine* e) {
   if (hp.ready) return ASZ_OK;
   const size_t G = (size_t)e->cfg.games;
   ASZ_CUDA(cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking));
+  ASZ_CUDA(cudaStreamCreateWithFlags(&hp.copy_out, cudaStreamNonBlocking));
   ASZ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hp.h_rows), 2 * 16 * sizeof(int32_t), cudaHostAllocDefault));
   for (int i = 0; i < 2; ++i) {
     ASZ_CUDA(cudaEventCreateWithFlags(&hp.copied[i], cudaEventDisableTiming));
     ASZ_CUDA(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
+    ASZ_CUDA(cudaEventCreateWithFlags(&hp.stepped[i], cudaEventDisableTiming));
     ASZ_CUDA(cudaMalloc(&hp.actions[i], G * 8));
     ASZ_CUDA(cudaMalloc(&hp.spawn[i], G * sizeof(int32_t)));
+    ASZ_CUDA(cudaMalloc(&hp.d_ended[i], G));
+    ASZ_CUDA(cudaMalloc(&hp.d_rewards[i], G * 8));
+    ASZ_CUDA(cudaMalloc(&hp.d_rows[i], 64));
   }
   hp.ready = true;
   return ASZ_OK;
@@ -685,10 +693,12 @@ void host_pipe_destroy(asz_engine* e) {
   for (int i = 0; i < 2; ++i) {
     if (hp.copied[i]) cudaEventDestroy(hp.copied[i]);
     if (hp.done[i]) cudaEventDestroy(hp.done[i]);
-    cudaFree(hp.actions[i]); cudaFree(hp.spawn[i]);
+    if (hp.stepped[i]) cudaEventDestroy(hp.stepped[i]);
+    cudaFree(hp.actions[i]); cudaFree(hp.spawn[i]); cudaFree(hp.d_ended[i]); cudaFree(hp.d_rewards[i]); cudaFree(hp.d_rows[i]);
   }
   if (hp.h_rows) cudaFreeHost(hp.h_rows);
   if (hp.copy) cudaStreamDestroy(hp.copy);
+  if (hp.copy_out) cudaStreamDestroy(hp.copy_out);
   hp = asz_engine::HostPipe();
 }
 }  // namespace asz
@@ -705,8 +715,11 @@ static void* pinned_alias(void* h) {
   return d;
 }
 
-int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
-                        const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, void* stream, int32_t* ticket) {
+// results_by_copy: the kernel writes the per-game results into the slot's device buffers and the engine's second copy stream
+// brings them to the host under the NEXT step's kernel (the pipelined calls); otherwise pinned result buffers are written by the
+// kernel itself over PCIe while it runs, which costs the kernel ~10 % but leaves nothing to do after it (the blocking call)
+static int host_submit(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions, const int32_t* h_spawn_cells,
+                       uint8_t* h_ended, int8_t* h_rewards, void* stream, int32_t* ticket, bool results_by_copy) {
   if (!e || !ticket) { set_error("null argument"); return ASZ_ERR_ARG; }
   DeviceGuard guard(e->device);
   NvtxRange nvtx("asz:env_submit_host");
@@ -731,13 +744,13 @@ int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const
   memset(&a, 0, sizeof a);
   a.flags = flags; a.spawn_mode = spawn_mode; a.d_actions = hp.actions[slot]; a.d_spawn_cells = hp.spawn[slot];
   a.d_planes = e->planes; a.d_row_ids = e->row_ids; a.max_rows = (int32_t)(G * (size_t)e->cfg.snakes); a.plane_pitch = e->pitch;
-  a.d_row_count = e->rows_ptr(); a.d_ended = e->ended; a.d_rewards = e->rewards;
-  // Result buffers in pinned (page-locked, UVA-mapped) host memory are written by the kernel itself, one posted PCIe write
+  a.d_row_count = e->rows_ptr(); a.d_ended = hp.d_ended[slot]; a.d_rewards = hp.d_rewards[slot];
+  // Result buffers in pinned (page-locked, UVA-mapped) host memory can be written by the kernel itself, one posted PCIe write
   // per game while the launch runs, instead of by two device->host copies after it (ASZ_HOST_ZEROCOPY=0 disables).
   static int zero_copy = -1;
   if (zero_copy < 0) { const char* v = getenv("ASZ_HOST_ZEROCOPY"); zero_copy = v ? atoi(v) : 1; }
   bool zc_ended = false, zc_rewards = false;
-  if (zero_copy && (flags & ASZ_STEP_TIC)) {
+  if (!results_by_copy && zero_copy && (flags & ASZ_STEP_TIC)) {
     if (void* d = pinned_alias(h_ended)) { a.d_ended = static_cast<uint8_t*>(d); zc_ended = true; }
     if (void* d = pinned_alias(h_rewards)) { a.d_rewards = static_cast<int8_t*>(d); zc_rewards = true; }
   }
@@ -745,14 +758,30 @@ int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const
   const int rc = asz_env_step(e, &a, stream);
   e->step_hints = e->device_hints;
   if (rc != ASZ_OK) return rc;
-  if (h_ended && !zc_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, e->ended, G, cudaMemcpyDeviceToHost, st));
-  if (h_rewards && !zc_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, e->rewards, G * 8, cudaMemcpyDeviceToHost, st));
-  ASZ_CUDA(cudaMemcpyAsync(hp.h_rows + 16 * slot, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  ASZ_CUDA(cudaEventRecord(hp.done[slot], st));
+  if (results_by_copy) {
+    // the row count leaves the hot word before the next launch zeroes it; everything else waits for the kernel on the out stream
+    ASZ_CUDA(cudaMemcpyAsync(hp.d_rows[slot], e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    ASZ_CUDA(cudaEventRecord(hp.stepped[slot], st));
+    ASZ_CUDA(cudaStreamWaitEvent(hp.copy_out, hp.stepped[slot], 0));
+    if (h_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, hp.d_ended[slot], G, cudaMemcpyDeviceToHost, hp.copy_out));
+    if (h_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, hp.d_rewards[slot], G * 8, cudaMemcpyDeviceToHost, hp.copy_out));
+    ASZ_CUDA(cudaMemcpyAsync(hp.h_rows + 16 * slot, hp.d_rows[slot], sizeof(int32_t), cudaMemcpyDeviceToHost, hp.copy_out));
+    ASZ_CUDA(cudaEventRecord(hp.done[slot], hp.copy_out));
+  } else {
+    if (h_ended && !zc_ended) ASZ_CUDA(cudaMemcpyAsync(h_ended, hp.d_ended[slot], G, cudaMemcpyDeviceToHost, st));
+    if (h_rewards && !zc_rewards) ASZ_CUDA(cudaMemcpyAsync(h_rewards, hp.d_rewards[slot], G * 8, cudaMemcpyDeviceToHost, st));
+    ASZ_CUDA(cudaMemcpyAsync(hp.h_rows + 16 * slot, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ASZ_CUDA(cudaEventRecord(hp.done[slot], st));
+  }
   hp.busy[slot] = true;
   hp.next = slot ^ 1;
   *ticket = slot;
   return ASZ_OK;
+}
+
+int asz_env_submit_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const uint8_t* h_actions,
+                        const int32_t* h_spawn_cells, uint8_t* h_ended, int8_t* h_rewards, void* stream, int32_t* ticket) {
+  return host_submit(e, flags, spawn_mode, h_actions, h_spawn_cells, h_ended, h_rewards, stream, ticket, true);
 }
 
 int asz_env_wait_host(asz_engine* e, int32_t ticket, int32_t* h_row_count) {
@@ -774,7 +803,7 @@ int asz_env_step_host(asz_engine* e, uint32_t flags, int32_t spawn_mode, const u
   NvtxRange nvtx("asz:env_step_host");
   cudaStream_t st = (cudaStream_t)stream;
   int32_t ticket = -1, rows = 0;
-  int rc = asz_env_submit_host(e, flags, spawn_mode, h_actions, h_spawn_cells, h_ended, h_rewards, stream, &ticket);
+  int rc = host_submit(e, flags, spawn_mode, h_actions, h_spawn_cells, h_ended, h_rewards, stream, &ticket, false);
   if (rc != ASZ_OK) return rc;
   rc = asz_env_wait_host(e, ticket, &rows);
   if (rc != ASZ_OK) return rc;

@@ -367,16 +367,23 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
-// FIRST = the first convolution (one tap over K = 32 im2col rows, 4 channel chunks); otherwise 9 taps x 16 chunks
+// FIRST = the first convolution (alpha_nnet.py:21-22, 3 input channels).  Its input is the same raster as every other layer's,
+// with ONE 16-byte channel chunk per position (3 real channels + 5 zeros; planes_to_raster_kernel), and its 9 taps are contracted
+// TWO PER MMA: in the K-major no-swizzle layout the second 16-byte K chunk of an operand lies LBO bytes after the first, and the
+// descriptor does not care what is there -- so with LBO = the row distance between two taps one K = 16 step multiplies the
+// (8 channels of tap 2j | 8 channels of tap 2j+1) of every row with the matching weight rows.  Five MMAs (the fifth pairs tap 8
+// with zero weights) instead of an im2col buffer: the layer reads 16 B per position where the im2col rows were 64 B, and the
+// separate im2col pass (write 64 B + read 64 B per position) is gone.  Weights: two chunks per tile, K steps 0..3 and K step 4.
 template <int HALO, bool PAIR, bool FIRST>
 __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, int n_tiles) {
   using SM = UmmaSmem<HALO, PAIR>;
   constexpr int NS = SM::b_stages;
-  constexpr int KC_HALF = FIRST ? 4 : 8;
+  constexpr int KC_HALF = FIRST ? 1 : 8;                           // channel chunks of A per half
   constexpr int HALVES = FIRST ? 1 : 2;
-  constexpr int TAPS = FIRST ? 1 : 9;
+  constexpr int TAPS = FIRST ? 2 : 9;                              // weight chunks per half (FIRST: K steps 0..3, K step 4)
   constexpr int TILE = PAIR ? 2 * SM::kSuper : SM::kSuper;         // positions per work unit
-  constexpr uint32_t chunk_bytes = (uint32_t)(KC_HALF * SM::b_rows * 16);
+  constexpr uint32_t chunk_bytes = (uint32_t)(8 * SM::b_rows * 16);          // a full weight chunk: 8 K chunks
+  constexpr uint32_t last_chunk_bytes = FIRST ? (uint32_t)(2 * SM::b_rows * 16) : chunk_bytes;   // FIRST: K step 4 alone
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
   unsigned char* sB = smem + SM::a_bytes;
@@ -421,7 +428,6 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
     if (lane == 0) {
       // ---- producer ----
       uint32_t stage = 0, phase = 0, it = 0;
-      const __nv_bfloat16* wt = p.wt + (PAIR ? (size_t)rank * (chunk_bytes / 2) : 0);
       constexpr size_t chunk_stride = (size_t)(PAIR ? 2 : 1) * (chunk_bytes / 2);        // bf16 elements between chunks
       for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
         const size_t row0 = (size_t)kGuard + (size_t)st * TILE + (size_t)rank * SM::kSuper - HALO;
@@ -436,11 +442,15 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
           }
 #pragma unroll 1
           for (int t = 0; t < TAPS; ++t) {
+            const uint32_t bytes = (t == TAPS - 1) ? last_chunk_bytes : chunk_bytes;
             mbar_wait(&b_empty[stage], phase ^ 1u);
-            mbar_expect_tx(&b_full[stage], chunk_bytes);
-            // single layout [tap][kc][128][8]: chunk (t, c) starts at (t * HALVES + c) * KC_HALF * 128 * 8
-            // pair layout   [tap][half][rank][KC_HALF][64][8]: chunk (t, c, rank) = ((t * HALVES + c) * 2 + rank) * chunk
-            bulk_g2s(sB + (size_t)stage * SM::b_chunk, wt + (size_t)(t * HALVES + c) * chunk_stride, chunk_bytes, &b_full[stage]);
+            mbar_expect_tx(&b_full[stage], bytes);
+            // single layout [tap][kc][128][8]: chunk (t, c) starts at (t * HALVES + c) * 8 * 128 * 8
+            // pair layout   [tap][half][rank][8][64][8]: chunk (t, c, rank) = ((t * HALVES + c) * 2 + rank) * chunk
+            // (FIRST: chunk 1 is short, and in the pair layout its two rank parts follow the two full parts of chunk 0)
+            const size_t off = (FIRST && PAIR && t == 1) ? (size_t)2 * (chunk_bytes / 2) + (size_t)rank * (last_chunk_bytes / 2)
+                                                         : (PAIR ? (size_t)rank * (chunk_bytes / 2) : 0) + (size_t)(t * HALVES + c) * chunk_stride;
+            bulk_g2s(sB + (size_t)stage * SM::b_chunk, p.wt + off, bytes, &b_full[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
         }
@@ -468,21 +478,40 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
           const uint32_t a_c = a_lo0 + (uint32_t)(c * KC_HALF * SM::rows + HALO);
 #pragma unroll
           for (int t = 0; t < TAPS; ++t) {
-            const int shift = (TAPS == 1) ? 0 : ((t / 3) - 1) * pitch + ((t % 3) - 1);
+            const int shift = FIRST ? 0 : ((t / 3) - 1) * pitch + ((t % 3) - 1);
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
             if (issuer) {
-              const uint32_t a_t = a_c + (uint32_t)shift;
               const uint32_t b_s = b_lo0 + stage * (uint32_t)(SM::b_chunk >> 4);
+              if (FIRST) {
+                // K step j = taps (2j, 2j+1): start address = the rows of tap 2j, LBO = the row distance to tap 2j+1
+                const uint32_t a_rows = ((smem_u32(sA) >> 4) & 0x3FFFu) + (uint32_t)HALO;
 #pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
+                for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-                for (int ks = 0; ks < KC_HALF / 2; ++ks) {
-                  const uint64_t ad = desc64(a_t + (uint32_t)(sub * kTileM + 2 * ks * SM::rows), desc_hi);
-                  const uint64_t bd = desc64(b_s + (uint32_t)(2 * ks * SM::b_rows), desc_hi);
-                  const uint32_t acc = (t == 0 && ks == 0) ? (uint32_t)c : 1u;
-                  if (PAIR) umma_bf16_pair(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
-                  else umma_bf16(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
+                  for (int ks = 0; ks < (t == 0 ? 4 : 1); ++ks) {
+                    const int j = t * 4 + ks, ta = 2 * j, tb = (2 * j + 1 < 9) ? 2 * j + 1 : 2 * j;
+                    const int sa = ((ta / 3) - 1) * pitch + ((ta % 3) - 1), sb = ((tb / 3) - 1) * pitch + ((tb % 3) - 1);
+                    const uint32_t lbo = (tb == ta) ? 1u : (uint32_t)(sb - sa);          // rows of 16 B = the LBO field's unit
+                    const uint64_t ad = desc64((a_rows + (uint32_t)(sa + sub * kTileM)) | (lbo << 16), desc_hi);
+                    const uint64_t bd = desc64(b_s + (uint32_t)(2 * ks * SM::b_rows), desc_hi);
+                    const uint32_t acc = (j == 0) ? 0u : 1u;
+                    if (PAIR) umma_bf16_pair(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
+                    else umma_bf16(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
+                  }
+                }
+              } else {
+                const uint32_t a_t = a_c + (uint32_t)shift;
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                  for (int ks = 0; ks < KC_HALF / 2; ++ks) {
+                    const uint64_t ad = desc64(a_t + (uint32_t)(sub * kTileM + 2 * ks * SM::rows), desc_hi);
+                    const uint64_t bd = desc64(b_s + (uint32_t)(2 * ks * SM::b_rows), desc_hi);
+                    const uint32_t acc = (t == 0 && ks == 0) ? (uint32_t)c : 1u;
+                    if (PAIR) umma_bf16_pair(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
+                    else umma_bf16(tmem_d + (uint32_t)(sub * kC), ad, bd, idesc, acc);
+                  }
                 }
               }
               if (PAIR) umma_commit_pair(&b_empty[stage]); else umma_commit(&b_empty[stage]);
@@ -628,6 +657,45 @@ __global__ void im2col_kernel(const float* __restrict__ planes, size_t plane_str
   }
 }
 
+// ---- input of the persistent first convolution: fp32 NHWC planes -> the raster with one 16-byte chunk per position (3 channels
+// + 5 zeros, bf16), zero at the padding positions -----------------------------------------------------------------------------
+__global__ void planes_to_raster_kernel(const float* __restrict__ planes, size_t plane_stride, int n_img, int real, int pitch, int img_stride,
+                                        __nv_bfloat16* __restrict__ out /* [P_tot][8] */) {
+  const int pos = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (pos >= n_img * img_stride) return;
+  const int n = pos / img_stride, rem = pos - n * img_stride;
+  const int y = rem / pitch, x = rem - y * pitch;
+  uint4 ov = make_uint4(0u, 0u, 0u, 0u);
+  if (y < real && x < real) {
+    const float* s = planes + (size_t)n * plane_stride + ((size_t)y * real + x) * 3;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+    ob[0] = __floats2bfloat162_rn(s[0], s[1]);
+    ob[1] = __floats2bfloat162_rn(s[2], 0.0f);
+  }
+  *reinterpret_cast<uint4*>(out + ((size_t)kGuard + (size_t)pos) * 8) = ov;
+}
+
+// first-layer weights for the tap-paired contraction: the caller's im2col layout [4 kc][128][8] (k = tap * 3 + channel, 27 of 32
+// used) -> K chunk t = the 8 channel slots of tap t (3 real), 10 chunks (tap 9 = zeros):
+//   single [10][128][8];   pair [chunk 0: rank][8][64][8] then [chunk 1: rank][2][64][8]
+__global__ void first_weight_layout_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst_single,
+                                           __nv_bfloat16* __restrict__ dst_pair) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);      // (tap chunk, cout)
+  if (i >= 10 * kC) return;
+  const int t = i / kC, cout = i - t * kC;
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int k = t * 3 + c;
+    v[c] = (t < 9 && c < 3) ? src[((size_t)(k >> 3) * kC + cout) * 8 + (k & 7)] : __float2bfloat16_rn(0.0f);
+  }
+  const uint4 pk = *reinterpret_cast<const uint4*>(v);
+  reinterpret_cast<uint4*>(dst_single)[(size_t)t * kC + cout] = pk;
+  const int r = cout / (kC / 2), co = cout % (kC / 2);
+  const size_t o = t < 8 ? ((size_t)r * 8 + t) * (kC / 2) + co : (size_t)2 * 8 * (kC / 2) + ((size_t)r * 2 + (t - 8)) * (kC / 2) + co;
+  reinterpret_cast<uint4*>(dst_pair)[o] = pk;
+}
+
 // ---- dense head: Flatten + Dense(128) + ReLU + Dense(3) + tanh (alpha_nnet.py:52-54), 8 images per CTA ------------------
 // The dense1 weights are re-laid out once on the padded raster ([img_stride][128], zero rows at padding positions), so the
 // head activations of an image are one contiguous run of img_stride floats (the epilogue wrote zeros at the padding).
@@ -755,6 +823,8 @@ struct asz_net {
   int variant = 3;                // 1 = one tile per CTA (conv_tile_kernel), 2 = persistent (conv_umma_kernel, one CTA per SM),
                                   // 3 = persistent over CTA pairs (conv_umma_kernel PAIR, cta_group::2)
   __nv_bfloat16* w_pair[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  __nv_bfloat16* w_first = nullptr;        // first-layer weights, tap-paired layout [10][128][8] (first_weight_layout_kernel)
+  __nv_bfloat16* w_first_pair = nullptr;   // ... split for CTA pairs
 };
 
 static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, float* d_values, int stop_layer, float* d_act, cudaStream_t st,
@@ -766,10 +836,11 @@ extern "C" {
 static int net_derive(asz_net* n, cudaStream_t st) {
   dense1_raster_kernel<<<(n->img_stride * 128 + 255) / 256, 256, 0, st>>>(n->w.dense1_w, n->real, n->pitch, n->img_stride, n->w1r);
   if (!cuda_ok(cudaGetLastError(), "dense1_raster_kernel")) return ASZ_ERR_CUDA;
-  for (int l = 0; l < 9; ++l) {
-    const int taps = l == 0 ? 1 : 9, kc_in = l == 0 ? 4 : kKC;
-    const int total = taps * kc_in * kC;
-    pair_weight_layout_kernel<<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(n->w.w_conv[l]), n->w_pair[l], taps, kc_in);
+  first_weight_layout_kernel<<<(10 * kC + 255) / 256, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(n->w.w_conv[0]), n->w_first, n->w_first_pair);
+  if (!cuda_ok(cudaGetLastError(), "first_weight_layout_kernel")) return ASZ_ERR_CUDA;
+  for (int l = 1; l < 9; ++l) {
+    const int total = 9 * kKC * kC;
+    pair_weight_layout_kernel<<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(n->w.w_conv[l]), n->w_pair[l], 9, kKC);
     if (!cuda_ok(cudaGetLastError(), "pair_weight_layout_kernel")) return ASZ_ERR_CUDA;
   }
   return ASZ_OK;
@@ -806,10 +877,9 @@ static int net_alloc(asz_net* n, const asz_net_weights* w, int32_t chunk_images)
   { int rc = configure_umma_kernels(); if (rc != ASZ_OK) return rc; }
   ASZ_CUDA(cudaFuncSetAttribute(dense_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   ASZ_CUDA(cudaMalloc(&n->w1r, (size_t)n->img_stride * 128 * sizeof(float)));
-  for (int l = 0; l < 9; ++l) {
-    const int taps = l == 0 ? 1 : 9, kc_in = l == 0 ? 4 : kKC;
-    ASZ_CUDA(cudaMalloc(&n->w_pair[l], (size_t)taps * kc_in * kC * 16));
-  }
+  for (int l = 1; l < 9; ++l) ASZ_CUDA(cudaMalloc(&n->w_pair[l], (size_t)9 * kKC * kC * 16));
+  ASZ_CUDA(cudaMalloc(&n->w_first, (size_t)10 * kC * 16));
+  ASZ_CUDA(cudaMalloc(&n->w_first_pair, (size_t)10 * kC * 16));
   { int rc = net_derive(n, nullptr); if (rc != ASZ_OK) return rc; }
   ASZ_CUDA(cudaDeviceSynchronize());
   return ASZ_OK;
@@ -844,6 +914,7 @@ int asz_net_destroy(asz_net* n) {
   for (int i = 0; i < 3; ++i) cudaFree(n->act[i]);
   cudaFree(n->col); cudaFree(n->head); cudaFree(n->w1r);
   for (int l = 0; l < 9; ++l) cudaFree(n->w_pair[l]);
+  cudaFree(n->w_first); cudaFree(n->w_first_pair);
   delete n;
   return ASZ_OK;
 }
@@ -865,7 +936,8 @@ static int launch_conv(asz_net* n, int layer, const __nv_bfloat16* in, const __n
     return cuda_ok(cudaGetLastError(), "conv_tile_kernel") ? ASZ_OK : ASZ_ERR_CUDA;
   }
   const bool pair = n->variant == 3;
-  if (pair) p.wt = n->w_pair[layer];
+  if (layer == 0) p.wt = pair ? n->w_first_pair : n->w_first;
+  else if (pair) p.wt = n->w_pair[layer];
   const bool big = n->pitch + 1 > 24;
   const int n_tiles = pair ? (p.P_real + 511) / 512 : (p.P_real + 255) / 256;
   const int grid = pair ? 2 * std::min(n_tiles, n->n_sm / 2) : std::min(n_tiles, n->n_sm);
@@ -935,8 +1007,13 @@ static int net_forward_impl(asz_net* n, const float* d_planes, int32_t count, fl
   for (int i0 = 0; i0 < count; i0 += per_pass) {
     const int m = std::min(per_pass, count - i0);
     const int P = m * n->img_stride;
-    im2col_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_planes + (size_t)i0 * plane, plane, m, n->real, n->pitch, n->img_stride, n->P_tot, n->col);
-    if (!cuda_ok(cudaGetLastError(), "im2col_kernel")) return ASZ_ERR_CUDA;
+    if (n->variant == 1) {     // one tile per CTA: im2col rows, one tap over K = 32
+      im2col_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_planes + (size_t)i0 * plane, plane, m, n->real, n->pitch, n->img_stride, n->P_tot, n->col);
+      if (!cuda_ok(cudaGetLastError(), "im2col_kernel")) return ASZ_ERR_CUDA;
+    } else {                   // persistent kernels: the 8-channel raster, taps contracted two per MMA
+      planes_to_raster_kernel<<<(P + 255) / 256, 256, 0, st>>>(d_planes + (size_t)i0 * plane, plane, m, n->real, n->pitch, n->img_stride, n->col);
+      if (!cuda_ok(cudaGetLastError(), "planes_to_raster_kernel")) return ASZ_ERR_CUDA;
+    }
     int rc = launch_conv(n, 0, n->col, nullptr, n->act[0], false, m, st);          // alpha_nnet.py:21-22
     if (rc != ASZ_OK) return rc;
     if (stop_layer == 0) return dump(n->act[0], nullptr, m);

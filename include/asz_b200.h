@@ -104,7 +104,9 @@ typedef struct {
   int32_t max_rows;
   int32_t* d_row_count;          /* [1] number of rows written by this call (the call zeroes it first) */
   uint8_t* d_ended;              /* [G] 1 when the game ended in this tic (may be NULL) */
-  int8_t* d_rewards;             /* [G*8] final rewards of games that ended in this tic: 0 none, 1, -1 (may be NULL) */
+  int8_t* d_rewards;             /* [G*8] rewards after this tic per (game, snake id): 1 winner, -1 dead, 0 alive or no such snake
+                                    (game.py:162-203); final where d_ended[g] = 1; all 0 for a game that was finished before
+                                    this tic and was not stepped (may be NULL) */
   int32_t row_base;              /* rows are written at [row_base, row_base + n) of d_planes / d_row_ids / d_keys; max_rows
                                     stays the absolute capacity (rows past it are dropped, *d_row_count still counts them) */
   int32_t plane_pitch;           /* floats between consecutive rows of d_planes: 0 (or asz_plane_floats) = dense rows;
