@@ -430,23 +430,29 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]      # one event per launch: a slow regime shows
     barrier()
     ev0.record()
-    step_ev[0].record()
     for i in range(K):
         eng.step(**kw)
-        step_ev[i + 1].record()
     ev1.record()
     if rank == 0:
         sampler.sample_now()      # the K launches are queued and executing: a sample from this thread is inside the region
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    t_after = eng.totals()
+    # per-launch percentiles from a second, untimed pass with an event after every launch (the events themselves cost ~1 us per
+    # launch, which is why they are not in the timed region): a launch-time distribution with two modes would show here
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    step_ev[0].record()
+    for i in range(K):
+        eng.step(**kw)
+        step_ev[i + 1].record()
+    torch.cuda.synchronize()
     per_launch = np.array([step_ev[i].elapsed_time(step_ev[i + 1]) * 1e3 for i in range(K)])      # us, includes the 2 us memset
     launch_us = {"p05": float(np.percentile(per_launch, 5)), "p50": float(np.median(per_launch)), "p95": float(np.percentile(per_launch, 95)),
-                 "max": float(per_launch.max()), "what": "CUDA events around every launch of the timed region (counter memset + kernel)"}
-    t_after = eng.totals()
+                 "max": float(per_launch.max()), "what": "CUDA events around every launch of a second pass of K launches right after the "
+                                                          "timed region (counter memset + kernel + the event)"}
     steps_local = t_after["tics"] - t_before["tics"]
     planes_local = t_after["planes"] - t_before["planes"]
 
