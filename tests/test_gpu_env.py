@@ -263,7 +263,10 @@ def test_food_chance_zero_never_spawns():
 
 @pytest.mark.parametrize("side,S,dec,G,tics", [(11, 4, 1, 4096, 120), (7, 4, 9, 1024, 80), (19, 8, 1, 512, 150),
                                                (11, 2, 3, 1000, 60), (7, 8, 1, 333, 60),
-                                               (11, 4, 1, 65536, 24)])      # BASELINE.json configs[1] at full size
+                                               (11, 4, 1, 65536, 24),       # BASELINE.json configs[1] at full size
+                                               # odd game counts just above two games per resident warp: scheduling tickets of two
+                                               # games, single games at the end of the launch and an odd last game, on every board size
+                                               (11, 4, 1, 9001, 30), (19, 8, 1, 3001, 20), (7, 4, 9, 8001, 24)])
 def test_native_run_against_oracle(side, S, dec, G, tics):
     """Seeded native runs (engine RNG for layouts, actions and food; auto reset): every game's final state, the
     totals and an order-free checksum over every plane written must equal the oracle's, bit for bit."""
