@@ -56,7 +56,6 @@ try:
 except Exception:
     pass
 gbs = bytes_per_launch / (tot_us / n) / 1e3
-print("   L2 monitor: %s" % {k: v for k, v in t1.items() if k.startswith("l2_")})
 print("%s %s: %d launches, %.1f us/launch (events per launch: median %.1f, p05 %.1f, p95 %.1f, max %.1f) | %.0f MB algorithmic per launch, "
       "%.0f GB/s = %.3f of %.0f GB/s | %.3e env steps/s" % (os.environ.get("ASZ_LIB", "libasz_b200.so"), "dense" if dense else "pitched", n, tot_us / n,
        np.median(d), np.percentile(d, 5), np.percentile(d, 95), d.max(), bytes_per_launch / 1e6, gbs, gbs / peak, peak, tics / (tot_us * 1e-6)))
