@@ -592,6 +592,7 @@ int asz_engine_create(asz_engine** out, const asz_config* cfg) {
 int asz_engine_destroy(asz_engine* e) {
   if (!e) return ASZ_OK;
   DeviceGuard guard(e->device);
+  cudaDeviceSynchronize();   // launches and copies still in flight (asz_env_submit_host never waited for) use the buffers freed below
   search_destroy(e);
   records_destroy(e);
   host_pipe_destroy(e);

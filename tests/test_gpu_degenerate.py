@@ -108,3 +108,28 @@ def test_argument_errors_are_reported():
     with pytest.raises(AszError):
         eng.search(value_fn=None)                       # the engine was created without a search configuration
     eng.close()
+
+
+def test_host_pipeline_edge_cases():
+    """asz_env_submit_host / asz_env_wait_host at the edges: one game, an odd number of games, pageable result buffers, missing
+    inputs, and an engine closed while a step is still in flight."""
+    import torch
+    from alphasnake_zero_b200.engine import AszError
+    for G in (1, 3):
+        a, b = _engine(side=7, snakes=2, games=G, seed=4), _engine(side=7, snakes=2, games=G, seed=4)
+        a.reset(); b.reset()
+        acts = torch.ones(G, 8, dtype=torch.uint8).pin_memory()
+        end_pin = torch.zeros(G, dtype=torch.uint8).pin_memory(); rew_pin = torch.zeros(G, 8, dtype=torch.int8).pin_memory()
+        end_pg = torch.zeros(G, dtype=torch.uint8); rew_pg = torch.zeros(G, 8, dtype=torch.int8)        # pageable
+        for _ in range(12):
+            ra = a.wait_host(a.submit_host(acts, end_pin, rew_pin, spawn_mode=2, auto_reset=True))
+            rb = b.wait_host(b.submit_host(acts, end_pg, rew_pg, spawn_mode=2, auto_reset=True))
+            assert ra == rb
+            assert torch.equal(end_pin, end_pg) and torch.equal(rew_pin, rew_pg)
+        with pytest.raises(AszError):
+            a.submit_host(None, end_pin, rew_pin, spawn_mode=2)                  # a tic with caller-supplied moves needs them
+        with pytest.raises(AszError):
+            a.submit_host(acts, end_pin, rew_pin, spawn_mode=1)                  # replayed spawns need the cells
+        a.submit_host(acts, end_pin, rew_pin, spawn_mode=2)                      # ... and never waited for
+        a.close(); b.close()
+    torch.cuda.synchronize()
