@@ -347,10 +347,10 @@ struct UmmaSmem {
   static constexpr size_t a_bytes = (size_t)kKC * rows * 16;       // one halo tile, managed as two channel halves
   static constexpr int b_rows = PAIR ? kC / 2 : kC;                // output channels whose weights this CTA holds
   static constexpr size_t b_chunk = (size_t)8 * b_rows * 16;       // half a tap: 16 KB (8 KB per CTA of a pair)
-  static constexpr int max_stages = 16;
+  static constexpr int max_stages = 18;                            // 18 = every weight chunk of a 3x3 layer (9 taps x 2 channel halves)
   static constexpr size_t tail = 3 * kC * sizeof(float) + (8 + 2 * max_stages) * sizeof(uint64_t) + 64;
   static constexpr int raw_stages = (int)((232448 - a_bytes - tail) / b_chunk);
-  static constexpr int b_stages = raw_stages > max_stages ? max_stages : raw_stages;   // 9 / 8 single, 16 pair
+  static constexpr int b_stages = raw_stages > max_stages ? max_stages : raw_stages;   // 9 / 8 single; pair: 18 (HALO 24) / 17 (HALO 40)
   static constexpr size_t total = a_bytes + b_stages * b_chunk + tail;
 };
 
@@ -384,6 +384,10 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
   constexpr int TILE = PAIR ? 2 * SM::kSuper : SM::kSuper;         // positions per work unit
   constexpr uint32_t chunk_bytes = (uint32_t)(8 * SM::b_rows * 16);          // a full weight chunk: 8 K chunks
   constexpr uint32_t last_chunk_bytes = FIRST ? (uint32_t)(2 * SM::b_rows * 16) : chunk_bytes;   // FIRST: K step 4 alone
+  // RESW: the CTA's half of the layer's weights (9 taps x 2 halves x 8 KB = 144 KB) fits next to the halo tile (11x11 boards, CTA
+  // pairs): it is loaded ONCE per launch and stays resident, instead of streaming through the stage ring once per super-tile
+  // (52 times per CTA and layer at 4,096 images).  Stage index = chunk index t * HALVES + c; b_full[0] is the only weight barrier.
+  constexpr bool RESW = PAIR && !FIRST && NS >= TAPS * HALVES;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
   unsigned char* sB = smem + SM::a_bytes;
@@ -429,6 +433,14 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
       // ---- producer ----
       uint32_t stage = 0, phase = 0, it = 0;
       constexpr size_t chunk_stride = (size_t)(PAIR ? 2 : 1) * (chunk_bytes / 2);        // bf16 elements between chunks
+      if constexpr (RESW) {
+        if (first_tile < n_tiles) {
+          mbar_expect_tx(&b_full[0], (uint32_t)(TAPS * HALVES) * chunk_bytes);
+#pragma unroll 1
+          for (int ch = 0; ch < TAPS * HALVES; ++ch)
+            bulk_g2s(sB + (size_t)ch * SM::b_chunk, p.wt + (size_t)rank * (chunk_bytes / 2) + (size_t)ch * chunk_stride, chunk_bytes, &b_full[0]);
+        }
+      }
       for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
         const size_t row0 = (size_t)kGuard + (size_t)st * TILE + (size_t)rank * SM::kSuper - HALO;
 #pragma unroll 1
@@ -440,6 +452,7 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
             const int kc = c * KC_HALF + k;
             bulk_g2s(sA + (size_t)kc * SM::rows * 16, p.in + ((size_t)kc * p.P_tot + row0) * 8, SM::rows * 16, &a_full[c]);
           }
+          if constexpr (!RESW) {
 #pragma unroll 1
           for (int t = 0; t < TAPS; ++t) {
             const uint32_t bytes = (t == TAPS - 1) ? last_chunk_bytes : chunk_bytes;
@@ -452,6 +465,7 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
                                                          : (PAIR ? (size_t)rank * (chunk_bytes / 2) : 0) + (size_t)(t * HALVES + c) * chunk_stride;
             bulk_g2s(sB + (size_t)stage * SM::b_chunk, p.wt + off, bytes, &b_full[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
+          }
           }
         }
       }
@@ -466,6 +480,9 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
       constexpr uint32_t idesc = PAIR ? kIdescPair : kIdesc;
       const int pitch = p.pitch;
       uint32_t stage = 0, phase = 0, it = 0;
+      if constexpr (RESW) {
+        if (first_tile < n_tiles) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }   // the resident weights of both CTAs have landed
+      }
       for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
         const uint32_t buf = it & 1u;
         mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // the epilogue(s) have drained this accumulator pair
@@ -479,10 +496,12 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
 #pragma unroll
           for (int t = 0; t < TAPS; ++t) {
             const int shift = FIRST ? 0 : ((t / 3) - 1) * pitch + ((t % 3) - 1);
-            mbar_wait(&b_full[stage], phase);
-            tc_fence_after();
+            if constexpr (!RESW) {
+              mbar_wait(&b_full[stage], phase);
+              tc_fence_after();
+            }
             if (issuer) {
-              const uint32_t b_s = b_lo0 + stage * (uint32_t)(SM::b_chunk >> 4);
+              const uint32_t b_s = b_lo0 + (RESW ? (uint32_t)(t * HALVES + c) : stage) * (uint32_t)(SM::b_chunk >> 4);
               if (FIRST) {
                 // K step j = taps (2j, 2j+1): start address = the rows of tap 2j, LBO = the row distance to tap 2j+1
                 const uint32_t a_rows = ((smem_u32(sA) >> 4) & 0x3FFFu) + (uint32_t)HALO;
@@ -514,10 +533,10 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
                   }
                 }
               }
-              if (PAIR) umma_commit_pair(&b_empty[stage]); else umma_commit(&b_empty[stage]);
+              if constexpr (!RESW) { if (PAIR) umma_commit_pair(&b_empty[stage]); else umma_commit(&b_empty[stage]); }
             }
             __syncwarp();
-            if (++stage == NS) { stage = 0; phase ^= 1u; }
+            if constexpr (!RESW) { if (++stage == NS) { stage = 0; phase ^= 1u; } }
           }
           if (issuer) { if (PAIR) umma_commit_pair(&a_empty[c]); else umma_commit(&a_empty[c]); }
         }
@@ -527,16 +546,21 @@ __global__ void __launch_bounds__(320, 1) conv_umma_kernel(const ConvParams p, i
     } else if (lane == 0) {
       // ---- relay of rank 1: tell rank 0's full barriers that this CTA's operands have landed ----
       uint32_t stage = 0, phase = 0, it = 0;
+      if constexpr (RESW) {
+        if (first_tile < n_tiles) { mbar_wait(&b_full[0], 0u); mbar_arrive_cluster(mapa_u32(smem_u32(&b_full[0]), 0)); }
+      }
       for (int st = first_tile; st < n_tiles; st += tile_step, ++it) {
 #pragma unroll 1
         for (int c = 0; c < HALVES; ++c) {
           mbar_wait(&a_full[c], it & 1u);
           mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[c]), 0));
+          if constexpr (!RESW) {
 #pragma unroll 1
           for (int t = 0; t < TAPS; ++t) {
             mbar_wait(&b_full[stage], phase);
             mbar_arrive_cluster(mapa_u32(smem_u32(&b_full[stage]), 0));
             if (++stage == NS) { stage = 0; phase ^= 1u; }
+          }
           }
         }
       }
