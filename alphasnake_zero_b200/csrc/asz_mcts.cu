@@ -261,33 +261,50 @@ __global__ void __launch_bounds__(WARPS * 32) search_step_kernel(const SearchPar
   if (lane < 8 && !sn.alive) p.row_slot[ri] = kNoRow;
   CellView<G> cv;
   warp_cell_view<G>(sb, sn, cv);
+  // Pass 1: key and probe of every live snake (lane 0 probes, one snake after the other: parallel lanes on diverged probe paths
+  // were measured slower); lane vs keeps its snake's result.  Then ONE returning atomic for the sub-game's rows of the eval batch
+  // instead of one per miss (same-address returning atomics are served one after the other by their L2 slice).
+  // Pass 2: the planes of the misses.
   unsigned rest = live_mask;
   int n_rows = 0, n_new = 0;
+  uint32_t my_slot = kNoRow; int my_new = 0;
+  uint64_t my_k0 = 0ull, my_k1 = 0ull;
   while (rest) {
     const int vs = __ffs(rest) - 1;
     rest &= rest - 1;
     uint64_t k0, k1;
     warp_encode<G, true>(cv, sn, vs, stage, nullptr, 0, &k0, &k1);
-    uint32_t slot = kNoRow; int is_new = 0, eidx = -1;
+    uint32_t slot = kNoRow; int is_new = 0;
     if (lane == 0) {
       const ProbeResult pr = table_probe(p.tab, k0, k1, p.root_turn, p.D, p.stats);
       slot = pr.slot; is_new = pr.is_new ? 1 : 0;
-      if (is_new) {
-        eidx = atomicAdd(p.n_miss, 1);
-        if (eidx < p.max_rows) {
-          p.eval_slot[eidx] = slot; p.eval_keys[2 * (size_t)eidx] = k0; p.eval_keys[2 * (size_t)eidx + 1] = k1;
-          p.tab.eval[slot] = eidx;
-        } else { eidx = -1; }
-      }
-      p.row_slot[(size_t)sub * 8 + vs] = slot;
-      p.row_new[(size_t)sub * 8 + vs] = (uint8_t)is_new;
     }
-    eidx = __shfl_sync(kFull, eidx, 0);
-    if (eidx >= 0) {
-      warp_encode<G, false>(cv, sn, vs, stage, p.eval_planes, (size_t)eidx * G::PLANE, nullptr, nullptr);
-      ++n_new;
-    }
+    slot = __shfl_sync(kFull, slot, 0); is_new = __shfl_sync(kFull, is_new, 0);
+    if (lane == vs) { my_slot = slot; my_new = is_new; my_k0 = k0; my_k1 = k1; }
     ++n_rows;
+  }
+  const unsigned new_mask = __ballot_sync(kFull, my_new != 0);
+  int eidx = -1;
+  if (new_mask) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(p.n_miss, __popc(new_mask));
+    base = __shfl_sync(kFull, base, 0);
+    if (my_new) {
+      eidx = base + __popc(new_mask & ((1u << lane) - 1u));
+      if (eidx < p.max_rows) {
+        p.eval_slot[eidx] = my_slot; p.eval_keys[2 * (size_t)eidx] = my_k0; p.eval_keys[2 * (size_t)eidx + 1] = my_k1;
+        p.tab.eval[my_slot] = eidx;
+      } else { eidx = -1; }
+    }
+  }
+  if (lane < 8 && sn.alive) { p.row_slot[ri] = my_slot; p.row_new[ri] = (uint8_t)my_new; }
+  unsigned todo = __ballot_sync(kFull, eidx >= 0);
+  n_new = __popc(todo);
+  while (todo) {
+    const int vs = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int e = __shfl_sync(kFull, eidx, vs);
+    warp_encode<G, false>(cv, sn, vs, stage, p.eval_planes, (size_t)e * G::PLANE, nullptr, nullptr);
   }
   if (lane == 0) {
     atomicAdd(&p.stats[ST_VISITS], (unsigned long long)n_rows);
