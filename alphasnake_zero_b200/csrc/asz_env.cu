@@ -96,8 +96,7 @@ __device__ __forceinline__ void store_meta(uint32_t* gm, const Meta& m, int lane
 // Persistent: MINB CTAs per SM, every warp loops over games g = warp_global, warp_global + n_warps, ... so that the
 // staging buffers' wall background is written once per warp and bulk stores of one game overlap the tic of the next.
 // HINTS: plane stores carry an evict_first L2 policy and the game records (read and rewritten by every launch, 21 MB at
-// 65,536 games) an evict_last one.  Worth 4 % on the device-resident path; the host-buffer path (asz_env_step_host) runs
-// 25 % SLOWER with either hint (measured, tools/env_state_probe3.py), so it uses the plain instructions.
+// 65,536 games) an evict_last one (ASZ_ENV_HINTS / ASZ_ENV_HINTS_HOST = 0 select the plain instructions for experiments).
 // ACTS: the caller supplies the actions (p.actions); false = none are read (in-kernel random actions, or no tic at all).
 // PITCHED: the plane rows are PitchGeo::PITCH floats apart (32-byte aligned rows: the engine's own buffers) and a game's planes
 // are emitted by warp_encode_game_v3; false = dense rows of PLANE floats (a caller's tensor), warp_encode_v2 per plane.
@@ -484,21 +483,10 @@ struct EnvLaunch {
   }
 };
 
-// experiments (tools/env_bisect.py): ASZ_DEBUG_PAD="<index>:<MB>" inserts a dummy allocation before the index-th allocation of an engine
-static void debug_pad(int index) {
-  static int want = -2, mb = 0, seen_root = 0;
-  if (want == -2) { const char* v = getenv("ASZ_DEBUG_PAD"); want = -1; if (v) sscanf(v, "%d:%d", &want, &mb); }
-  (void)seen_root;
-  if (index == want && mb > 0) { void* p = nullptr; cudaMalloc(&p, (size_t)mb << 20); fprintf(stderr, "[asz] debug pad of %d MB before allocation %d\n", mb, index); }
-}
-
 int gameset_alloc(GameSet& gs, int n, int pc) {
   gs.n = n;
-  debug_pad(0);
   ASZ_CUDA(cudaMalloc(&gs.cells, (size_t)n * pc * sizeof(uint16_t)));
-  debug_pad(1);
   ASZ_CUDA(cudaMalloc(&gs.snakes, (size_t)n * 8 * sizeof(uint64_t)));
-  debug_pad(2);
   ASZ_CUDA(cudaMalloc(&gs.meta, (size_t)n * 8 * sizeof(uint32_t)));
   ASZ_CUDA(cudaMemset(gs.cells, 0, (size_t)n * pc * sizeof(uint16_t)));
   ASZ_CUDA(cudaMemset(gs.snakes, 0, (size_t)n * 8 * sizeof(uint64_t)));
@@ -509,8 +497,6 @@ void gameset_free(GameSet& gs) {
   cudaFree(gs.cells); cudaFree(gs.snakes); cudaFree(gs.meta);
   gs = GameSet();
 }
-
-constexpr int kWorkCounterAt = 320;   // ints
 
 static int pc_of(int side) { return side == 7 ? Geo<7>::PC : side == 11 ? Geo<11>::PC : Geo<19>::PC; }
 
@@ -545,24 +531,12 @@ static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   const size_t G = (size_t)cfg->games, rows = G * (size_t)cfg->snakes;
   int rc = gameset_alloc(e->root, cfg->games, e->pc);
   if (rc != ASZ_OK) return rc;
-  debug_pad(3);
   ASZ_CUDA(cudaMalloc(&e->planes, rows * (size_t)e->pitch * sizeof(float) + 32));
-  debug_pad(4);
   ASZ_CUDA(cudaMalloc(&e->row_ids, rows * sizeof(int32_t)));
-  debug_pad(5);
   // one 64-bit word: [0] rows of the last step, [1] the kernel's game scheduler (EnvParams::sched); the rest is padding
   ASZ_CUDA(cudaMalloc(&e->row_count, (size_t)8 << 20));
-  debug_pad(6);
-  ASZ_CUDA(cudaMalloc(&e->actions, G * 8));
-  ASZ_CUDA(cudaMalloc(&e->spawn_cells, G * sizeof(int32_t)));
-  ASZ_CUDA(cudaMalloc(&e->ended, G));
-  ASZ_CUDA(cudaMalloc(&e->rewards, G * 8));
-  debug_pad(10);
   ASZ_CUDA(cudaMalloc(&e->totals, 32 * sizeof(unsigned long long)));   // [0..15] totals, [16..23] profile build's cycle sums
   ASZ_CUDA(cudaMemset(e->totals, 0, 32 * sizeof(unsigned long long)));
-  ASZ_CUDA(cudaMemset(e->ended, 0, G));
-  ASZ_CUDA(cudaMemset(e->rewards, 0, G * 8));
-  ASZ_CUDA(cudaMemset(e->actions, 1, G * 8));
   if (cfg->max_breadth > 0) {
     rc = search_create(e);
     if (rc != ASZ_OK) return rc;
@@ -597,8 +571,7 @@ int asz_engine_destroy(asz_engine* e) {
   records_destroy(e);
   host_pipe_destroy(e);
   gameset_free(e->root);
-  cudaFree(e->planes); cudaFree(e->row_ids); cudaFree(e->row_count); cudaFree(e->actions); cudaFree(e->spawn_cells);
-  cudaFree(e->ended); cudaFree(e->rewards); cudaFree(e->totals);
+  cudaFree(e->planes); cudaFree(e->row_ids); cudaFree(e->row_count); cudaFree(e->totals);
   delete e;
   return ASZ_OK;
 }
