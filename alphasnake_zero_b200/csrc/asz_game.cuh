@@ -130,17 +130,21 @@ __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, 
     nh = off ? -1 : y * SIDE + x;
     sn.health -= health_dec;
   }
-  // 3. eat, first come in list order (game.py:121-127)
+  // 3. eat, first come in list order (game.py:121-127).  One __match_any_sync groups the snakes by the cell they move to (a dead
+  // or off-board snake gets a key of its own): the lower lanes of a group are the snakes that come first in list order, the other
+  // members are the head-on opponents of step 5.
   const bool onfood = was_alive && !off && sb[nh < 0 ? 0 : nh] == kFood;
-  bool earlier = false, shared = false, lose = false;
-  unsigned blocked = 0;   // head cells among this lane's cells (for the spawn's empty set)
-#pragma unroll 1   // rolled on purpose: the hot loop of env_step_kernel is larger than the 32 KB L1.5 instruction cache
-  for (int s2 = 0; s2 < kMaxSnakes; ++s2) {
-    if (s2 >= S) break;                                        // warp-uniform: snake slots >= S are never alive
-    const int nh2 = __shfl_sync(kFull, nh, s2);
-    const int al2 = __shfl_sync(kFull, (int)was_alive, s2);
-    if (al2 && nh2 >= 0) {
-      if (nh2 == nh && s2 < lane) earlier = true;
+  const unsigned same_cell = __match_any_sync(kFull, (was_alive && nh >= 0) ? nh : -1 - lane);
+  const bool earlier = (same_cell & ((1u << lane) - 1u)) != 0u;
+  bool shared = false, lose = false;
+  // head cells among this lane's cells (for the spawn's empty set): every live snake's new head, gathered lane by lane
+  unsigned blocked = 0;
+  {
+    unsigned movers = __ballot_sync(kFull, was_alive && nh >= 0);
+    while (movers) {                                           // warp-uniform: one trip per live snake
+      const int s2 = __ffs(movers) - 1;
+      movers &= movers - 1;
+      const int nh2 = __shfl_sync(kFull, nh, s2);
       if (nh2 / CPL == lane) blocked |= 1u << (nh2 - lane * CPL);
     }
   }
@@ -196,13 +200,16 @@ __device__ __forceinline__ TicResult warp_tic(uint16_t* sb, Snake& sn, Meta& m, 
     if (off) cause = 1;
     else if (cell_is_body(sb[nh])) cause = 2;
   }
-#pragma unroll 1   // rolled on purpose: the hot loop of env_step_kernel is larger than the 32 KB L1.5 instruction cache
-  for (int s2 = 0; s2 < kMaxSnakes; ++s2) {
-    if (s2 >= S) break;
-    const int nh2 = __shfl_sync(kFull, nh, s2);
-    const int al2 = __shfl_sync(kFull, (int)was_alive, s2);
-    const int len2 = __shfl_sync(kFull, sn.len, s2);
-    if (was_alive && !off && al2 && s2 != lane && nh2 == nh) { shared = true; if (sn.len <= len2) lose = true; }
+  // head-on (game.py:156-163): another snake moved to the same cell; the shorter or equal one loses.  Rare, so the lengths are
+  // only compared when some group has more than one member (warp-uniform branch)
+  shared = was_alive && !off && (same_cell & ~(1u << lane)) != 0u;
+  if (__any_sync(kFull, shared)) {
+#pragma unroll 1
+    for (int s2 = 0; s2 < kMaxSnakes; ++s2) {
+      if (s2 >= S) break;
+      const int len2 = __shfl_sync(kFull, sn.len, s2);
+      if (shared && s2 != lane && ((same_cell >> s2) & 1u) && sn.len <= len2) lose = true;
+    }
   }
   if (was_alive && cause == 0) {
     if (shared) { if (lose) cause = 3; }
