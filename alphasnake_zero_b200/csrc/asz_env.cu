@@ -204,8 +204,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
   };
   // one game: tic (results, in-place reset, record write-back) and its live snakes = the rows it needs
   // `stash` (game A of a pair): where the lanes' packed snake records wait for the encode; `pf_rec`: the record as unpacked
-  auto step_game = [&](int g, uint16_t* board, Snake& sn, Meta& m, unsigned& live_mask, int& n_rows, uint64_t* stash, uint64_t pf_rec) {
+  // `last` (the ticket's last game): the ticket's atomic -- rows of its games, next ticket -- is issued as soon as this game's rows are
+  // known, BEFORE its record is written back, so that the write-back covers part of the atomic's latency; `n_before` = rows of the
+  // ticket's earlier game
+  auto step_game = [&](int g, uint16_t* board, Snake& sn, Meta& m, unsigned& live_mask, int& n_rows, uint64_t* stash, uint64_t pf_rec,
+                       bool last, int n_before, int& row, int& nxt) {
     live_mask = 0u; n_rows = 0;
+    auto rows_and_ticket = [&]() {
+      if (enc && !(m.flags & 1u)) {
+        live_mask = __ballot_sync(kFull, sn.alive != 0);
+        n_rows = __popc(live_mask);
+      }
+      if (last && lane == 0) {
+        const unsigned long long v = atomicAdd(p.sched, (1ull << 32) | (unsigned long long)(unsigned)(n_before + n_rows));
+        row = (int)(uint32_t)v; nxt = n_warps + (int)(v >> 32);
+        s_wtot[warp][8] += (uint32_t)(n_before + n_rows);
+      }
+    };
     if ((p.flags & ASZ_STEP_TIC) && !(m.flags & 1u)) {
       int move = 1;
       uint32_t spawn_r[2] = {0u, 0u};
@@ -238,6 +253,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         }
       }
       if (r.ended && (p.flags & ASZ_STEP_AUTO_RESET)) warp_init_native<G>(board, sn, m, p.S, p.seed, (uint32_t)g, m.episode + 1);
+      rows_and_ticket();
       // write the record back
       {
         uint32_t* gc = reinterpret_cast<uint32_t*>(p.cells + (size_t)g * G::PC);
@@ -276,10 +292,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
         if (lane < 8 && p.rewards != nullptr) p.rewards[(size_t)g * 8 + lane] = 0;
       }
       if (stash != nullptr && lane < 8) stash[lane] = pf_rec;      // not stepped: the record as it was loaded
-    }
-    if (enc && !(m.flags & 1u)) {
-      live_mask = __ballot_sync(kFull, sn.alive != 0);
-      n_rows = __popc(live_mask);
+      rows_and_ticket();
     }
   };
   // planes of one game into rows [row, row + n_rows) (rows of a game stay contiguous, ascending snake id)
@@ -332,6 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
     Snake sn; Meta m;
     unsigned maskA = 0u, maskB = 0u;
     int nA = 0, nB = 0;
+    int row = 0, nxt = 0;
     // one copy of the tic and of the encode in the instruction stream, two trips each: the loop body is ~40 KB of SASS already,
     // beyond the 32 KB L1.5 instruction cache; unrolling either loop costs 20 - 45 % (218 / 197 / 240 us, measured)
 #pragma unroll 1
@@ -342,16 +356,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
       if (h == 0) { ASZ_PROF(0); }                // waiting for the prefetched record
       if (h + 1 < cnt) prefetch(gA + 1);          // B's record streams in while A is stepped
       unsigned mk; int nk;
-      step_game(gA + h, board, sn, m, mk, nk, (h + 1 < cnt) ? &s_stash[warp][0] : nullptr, rec0);
+      step_game(gA + h, board, sn, m, mk, nk, (h + 1 < cnt) ? &s_stash[warp][0] : nullptr, rec0, h + 1 == cnt, nA, row, nxt);
       if (h == 0) { maskA = mk; nA = nk; } else { maskB = mk; nB = nk; }
     }
-    ASZ_PROF(1);   // draws, tics, results, record write-backs
-    int row = 0, nxt = 0;
-    if (lane == 0) {
-      const unsigned long long v = atomicAdd(p.sched, (1ull << 32) | (unsigned long long)(unsigned)(nA + nB));
-      row = (int)(uint32_t)v; nxt = n_warps + (int)(v >> 32);
-      s_wtot[warp][8] += (uint32_t)(nA + nB);
-    }
+    ASZ_PROF(1);   // draws, tics, results, the ticket's atomic, record write-backs
     // the next ticket's first record streams in while this ticket's planes are encoded
     nxt = __shfl_sync(kFull, nxt, 0);
     ASZ_PROF(2);   // waiting for the scheduling word
