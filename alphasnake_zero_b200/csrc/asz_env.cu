@@ -464,7 +464,7 @@ struct EnvLaunch {
     const int blocks = std::min((p.G + WARPS - 1) / WARPS, p.n_sm * MINB);
     // the last `rounds` games of every warp are handed out one by one, everything before in pairs
     static int rounds = -1;
-    if (rounds < 0) { const char* v = getenv("ASZ_ENV_TAIL_ROUNDS"); rounds = v ? std::max(0, atoi(v)) : 2; }
+    if (rounds < 0) { const char* v = getenv("ASZ_ENV_TAIL_ROUNDS"); rounds = v ? std::max(0, atoi(v)) : 3; }   // 2: +2.5 us, 4 and 6: the same as 3
     EnvParams q = p;
     q.pair_tickets = std::max(0, p.G - rounds * blocks * WARPS) / 2;
     q.n_tickets = p.G - q.pair_tickets;
