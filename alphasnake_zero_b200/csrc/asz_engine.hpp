@@ -70,7 +70,9 @@ struct asz_engine {
   int32_t* row_ids = nullptr;     // [G*S]
   int32_t* row_count = nullptr;   // 8 MB buffer that holds the kernel's one hot 64-bit word (rows handed out | tickets handed out)
   size_t sched_off = 0;           // byte offset of that word (tools/env_hot.py moves it around to map the L2 slices' atomic rates)
-  int32_t* rows_ptr() const { return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(row_count) + sched_off); }
+  int sched_flip = 0;             // launches alternate between the word at sched_off and the one 64 bytes behind it (asz_env_step)
+  // the word of the LAST launch: its low half is that launch's row count
+  int32_t* rows_ptr() const { return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(row_count) + sched_off + (sched_flip ? 64 : 0)); }
   unsigned long long* totals = nullptr;  // [8]
   int device_hints = 1, host_hints = 0, step_hints = 1;   // L2 policy hints of env_step_kernel (asz_env.cu)
   // asz_env_submit_host / asz_env_wait_host: two steps in flight, the inputs of the next one copied under the kernel of this one

@@ -44,6 +44,8 @@ struct EnvParams {
                                // kernel's dynamic scheduler).  A game takes both with a single atomicAdd: the two counters used to
                                // be separate words, and whenever their lines happened to share an L2 slice (a property of the
                                // physical placement, i.e. of the process) every launch ran at ~237 us instead of ~155 us
+  unsigned long long* sched_next;   // the word the NEXT launch uses: zeroed by this one (the engine alternates between two words, so no
+                                    // memset node sits between two launches)
   unsigned long long* prof;   // ASZ_ENV_PROFILE builds only: per-phase cycle sums (tools/env_profile.py)
   int hints;           // 1: L2 policies (planes evict_first, game records evict_last), 0: default policy everywhere
   int device, n_sm;    // the engine's device and its multiprocessor count (grid size of the persistent kernel)
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) env_step_kernel(const EnvPar
     fill_wall_pattern(stage0 + SM::WSTAGE, SM::WSTAGE, lane, 32);
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.sched_next = 0ull;
   EncodeCtx<G> ctx;
   EncodeCtxP<G> ctxp;
   // p.hints (experiments): 1 = both policies, 2 = planes evict_first only, 3 = records evict_last only
@@ -541,8 +544,9 @@ static int engine_alloc(asz_engine* e, const asz_config* cfg) {
   if (rc != ASZ_OK) return rc;
   ASZ_CUDA(cudaMalloc(&e->planes, rows * (size_t)e->pitch * sizeof(float) + 32));
   ASZ_CUDA(cudaMalloc(&e->row_ids, rows * sizeof(int32_t)));
-  // one 64-bit word: [0] rows of the last step, [1] the kernel's game scheduler (EnvParams::sched); the rest is padding
+  // the kernel's scheduling word (low half: rows of the step, high half: tickets handed out) and its alternate; the rest is padding
   ASZ_CUDA(cudaMalloc(&e->row_count, (size_t)8 << 20));
+  ASZ_CUDA(cudaMemset(e->row_count, 0, (size_t)8 << 20));            // every candidate pair of scheduling words starts at zero
   ASZ_CUDA(cudaMalloc(&e->totals, 32 * sizeof(unsigned long long)));   // [0..15] totals, [16..23] profile build's cycle sums
   ASZ_CUDA(cudaMemset(e->totals, 0, 32 * sizeof(unsigned long long)));
   if (cfg->max_breadth > 0) {
@@ -625,13 +629,19 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
     set_error("plane_pitch must be 0 (dense rows) or asz_plane_pitch()"); return ASZ_ERR_ARG;
   }
   p.pitched = (a->plane_pitch == e->pitch && e->pitch != e->plane) ? 1 : 0;
-  // rows are always counted in the engine's own counter (its L2 slice is known not to be the work counter's; a caller's
-  // 4-byte buffer could land anywhere) and copied to the caller's d_row_count after the launch
-  p.row_count = e->rows_ptr();
+  // Rows are always counted in the engine's own scheduling word and copied to the caller's d_row_count after the launch.  The
+  // engine alternates between two words: this launch uses the one the previous launch zeroed and zeroes the other one (whose row
+  // count every stream-ordered reader of the previous launch has consumed by the time this kernel runs), so there is no memset
+  // node between two launches.
+  const bool own_count = a->d_row_count != nullptr && reinterpret_cast<const char*>(a->d_row_count) >= reinterpret_cast<const char*>(e->row_count) &&
+                         reinterpret_cast<const char*>(a->d_row_count) < reinterpret_cast<const char*>(e->row_count) + ((size_t)8 << 20);
+  const int flip = e->sched_flip ^ 1;                                // committed when the launch has been enqueued
+  char* const pair = reinterpret_cast<char*>(e->row_count) + e->sched_off;
+  p.sched = reinterpret_cast<unsigned long long*>(pair + (flip ? 64 : 0));       // low word = the row count the callers read
+  p.sched_next = reinterpret_cast<unsigned long long*>(pair + (flip ? 0 : 64));
+  p.row_count = reinterpret_cast<int32_t*>(p.sched);
   p.ended = a->d_ended; p.rewards = a->d_rewards; p.totals = e->totals; p.prof = e->totals + 16;
-  p.sched = reinterpret_cast<unsigned long long*>(e->rows_ptr());   // low word = the row count the callers read
   p.hints = e->step_hints;
-  ASZ_CUDA(cudaMemsetAsync(p.sched, 0, sizeof(unsigned long long), st));
   int rc;
   switch (e->cfg.side) {
     case 7: rc = EnvLaunch<7>::step(p, st); break;
@@ -639,7 +649,8 @@ int asz_env_step(asz_engine* e, const asz_step_args* a, void* stream) {
     default: rc = EnvLaunch<19>::step(p, st); break;
   }
   if (rc != ASZ_OK) return rc;
-  if (a->d_row_count && a->d_row_count != e->rows_ptr())
+  e->sched_flip = flip;
+  if (a->d_row_count && !own_count)
     ASZ_CUDA(cudaMemcpyAsync(a->d_row_count, e->rows_ptr(), sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return ASZ_OK;
 }
@@ -837,6 +848,8 @@ int asz_internal_set_hot_word(asz_engine* e, int32_t k) {
   DeviceGuard guard(e->device);
   ASZ_CUDA(cudaDeviceSynchronize());
   e->sched_off = hot_word_offset(k);
+  e->sched_flip = 0;
+  ASZ_CUDA(cudaMemset(reinterpret_cast<char*>(e->row_count) + e->sched_off, 0, 128));   // both words of the pair start at zero
   return ASZ_OK;
 }
 int asz_internal_state(asz_engine* e, void** d_ptrs) {
