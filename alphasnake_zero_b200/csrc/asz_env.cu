@@ -39,11 +39,11 @@ struct EnvParams {
   const uint8_t* actions; const int32_t* spawn_cells;
   float* planes; int32_t* row_ids; uint64_t* keys; int max_rows; int32_t* row_count;
   uint8_t* ended; int8_t* rewards; unsigned long long* totals;
-  unsigned long long* sched;   // ONE 64-bit word, zeroed before the launch: low half = rows handed out so far (the batch's row
-                               // allocator), high half = games handed out beyond the warps' static first game (the persistent
-                               // kernel's dynamic scheduler).  A game takes both with a single atomicAdd: the two counters used to
-                               // be separate words, and whenever their lines happened to share an L2 slice (a property of the
-                               // physical placement, i.e. of the process) every launch ran at ~237 us instead of ~155 us
+  unsigned long long* sched;   // ONE 64-bit word, zero when the launch starts: low half = rows handed out so far (the batch's row
+                               // allocator), high half = tickets handed out beyond the warps' static first ticket (the persistent
+                               // kernel's dynamic scheduler).  A ticket takes both with a single returning atomicAdd; an L2 slice
+                               // serves such atomics on one word one after the other (2.3 - 3.6 ns each), which is why there is
+                               // one per ticket of two games and not one (or two, round 1) per game
   unsigned long long* sched_next;   // the word the NEXT launch uses: zeroed by this one (the engine alternates between two words, so no
                                     // memset node sits between two launches)
   unsigned long long* prof;   // ASZ_ENV_PROFILE builds only: per-phase cycle sums (tools/env_profile.py)
